@@ -1,0 +1,163 @@
+/*
+ * b200resnet.h — C ABI of libb200resnet.so: the sm_100a kernels behind the ResNet/WRN training step.
+ *
+ * This is the drop-in boundary for the hot path of lucaslingle/pytorch_ddp_resnet. The reference has
+ * no native code of its own: every arithmetic op on its path is a torch (ATen/cuDNN/cuBLAS) call made
+ * from Python. Each entry point below names the reference call site (file:line under the reference
+ * repo) whose ATen dispatch it replaces. The host-side mirror in pytorch_ddp_resnet_b200/ binds these
+ * through ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C linkage, POD arguments only (device pointers, ints, floats, a cudaStream_t as void*);
+ *   - every call returns 0 on success, non-zero on error; b200_last_error() gives the message
+ *     (thread-local). Nothing throws, nothing calls exit();
+ *   - all launches are asynchronous on the given stream; no call synchronises the device;
+ *   - no allocation inside: the caller owns every buffer, including workspaces whose size the
+ *     matching *_workspace_bytes() query returns;
+ *   - activations are NHWC bf16 ("channels_last" physical layout of an NCHW-shaped torch tensor);
+ *     conv filters are KRSC (physical layout of an OIHW-shaped channels_last torch tensor):
+ *     fp32 masters, bf16 working copies in KRSC and CRSK (transposed) order made by b200_weight_prep;
+ *   - statistics, affine parameters, optimizer state and weight gradients are fp32.
+ */
+#ifndef B200RESNET_H_
+#define B200RESNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* a cudaStream_t */
+
+/* conv algorithm selector */
+enum { B200_ALGO_AUTO = 0, B200_ALGO_DIRECT = 1, B200_ALGO_TC = 2 };
+/* which conv pass a workspace query refers to */
+enum { B200_PASS_FPROP = 0, B200_PASS_DGRAD = 1, B200_PASS_WGRAD = 2 };
+/* skip-connection addressing for the fused BN kernels */
+enum {
+  B200_SKIP_NONE = 0,
+  B200_SKIP_SAME = 1,       /* skip tensor has the output's shape                                  */
+  B200_SKIP_SUBSAMPLE_PAD = 2 /* skip is [N,2H,2W,Cs]: read at (2h,2w), channels >= Cs read as zero */
+};
+
+/* ---- library ------------------------------------------------------------------------------- */
+int b200_version(void);
+const char* b200_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (sm_100a code is the only code here). */
+int b200_device_check(void);
+/* Returns 1 when the tcgen05 path supports the shape, else 0. Never fails. */
+int b200_conv2d_tc_supported(int pass, int N, int H, int W, int C, int K, int R, int S, int stride,
+                             int pad);
+
+/* ---- filters --------------------------------------------------------------------------------
+ * fp32 KRSC master -> bf16 KRSC (fprop, wgrad layout) and bf16 CRSK (dgrad operand).
+ * Replaces the per-call autocast weight cast of tc.nn.Conv2d (residual_block.py:34-57,129-159;
+ * resnet.py:69-75). Either output may be NULL. */
+int b200_weight_prep(const float* w_krsc, void* w_krsc_bf16, void* w_crsk_bf16, int K, int RS, int C,
+                     b200_stream_t stream);
+
+/* ---- convolution (aten::convolution / convolution_backward; call sites residual_block.py:73,78,
+ * 81,86,179-203,92,208 and resnet.py:69-75). Shapes: x [N,H,W,C], w [K,R,S,C], y [N,P,Q,K] with
+ * P = (H + 2*pad - R)/stride + 1. stride in {1,2}. --------------------------------------------- */
+size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int C, int K, int R, int S,
+                                   int stride, int pad, int algo);
+
+/* y = bf16( conv(x, w) [+ bias] ) ; if residual: y = bf16(y + residual)  (residual add of
+ * residual_block.py:96,212 fused into the epilogue). bias (fp32 [K]) and residual may be NULL. */
+int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias, const void* residual,
+                      void* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                      int algo, void* ws, size_t ws_bytes, b200_stream_t stream);
+
+/* dx = bf16( conv_transpose(dy, w) ) ; if addend: dx = bf16(dx + addend) (skip-path gradient).
+ * w_crsk is the transposed bf16 filter from b200_weight_prep. */
+int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx, int N, int H,
+                      int W, int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
+                      size_t ws_bytes, b200_stream_t stream);
+
+/* dw[K,R,S,C] (fp32) = sum over pixels of dy (x) x. dbias (fp32 [K], may be NULL) = sum of dy. */
+int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N, int H, int W,
+                      int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
+                      size_t ws_bytes, b200_stream_t stream);
+
+/* fp32 NCHW image batch -> bf16 NHWC (the x.to(device) + autocast input cast of training.py:94-96). */
+int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,
+                               b200_stream_t stream);
+
+/* ---- batch norm + activation + dropout + skip (aten::native_batch_norm, relu, native_dropout, add,
+ * constant_pad_nd, avg_pool2d(k=1,s=2); residual_block.py:58-65,69-98,175-214; resnet.py:111-115) -- */
+size_t b200_bn_workspace_bytes(int64_t rows, int C);
+
+/* Per-channel batch statistics of x [rows, C] (bf16): mean, invstd = rsqrt(biased var + eps).
+ * If running_mean/running_var are non-NULL they are updated in place with `momentum` and the
+ * unbiased variance; if num_batches_tracked (int64 scalar) is non-NULL it is incremented. */
+int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum, float* mean,
+                  float* invstd, float* running_mean, float* running_var,
+                  int64_t* num_batches_tracked, void* ws, size_t ws_bytes, b200_stream_t stream);
+
+/* y = dropout( act( (x - mean) * invstd * gamma + beta [+ skip] ) ).
+ * stat_is_var != 0: `invstd` holds a variance (eval mode, running stats) and rsqrt(var+eps) is applied.
+ * gamma/beta/mean/invstd NULL  => the affine/normalise step is skipped (plain act/dropout/add).
+ * relu: 0/1. dropout_p in [0,1): keep mask from the counter RNG keyed by (seed, element index).
+ * x is [N,H,W,C]; skip addressing per skip_mode (skip_C = channel count of the skip tensor). */
+int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const float* mean,
+                    const float* invstd, int stat_is_var, float eps, const float* gamma,
+                    const float* beta, const void* skip, int skip_mode, int skip_C, int relu,
+                    float dropout_p, uint64_t seed, b200_stream_t stream);
+
+/* Backward of b200_bn_act_fwd. y is the forward OUTPUT (its non-zero pattern is the relu mask; may
+ * be NULL when relu == 0), x the forward input, dy the gradient w.r.t. y. The dropout mask is
+ * regenerated from (seed, element index). With g = dy * dropmask * 1/(1-p) * relumask this produces
+ * dbeta = sum(g), dgamma = sum(g * xhat), dx (bf16) and, if dskip != NULL, g itself (the gradient
+ * flowing to the skip operand, output-shaped). If addend != NULL: dx = bf16(dx + addend) (same
+ * shape; the strided skip gradients use b200_upsample_add). gamma NULL => no normalisation (dx = g). */
+int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
+                    const void* addend, int64_t rows, int C, const float* mean, const float* invstd,
+                    const float* gamma, float* dgamma, float* dbeta, int relu, float dropout_p,
+                    uint64_t seed, void* ws, size_t ws_bytes, b200_stream_t stream);
+
+/* y[n,h,w,c] = x[n,2h,2w,c] (AvgPool2d(kernel 1, stride 2), residual_block.py:49,90,151,206). */
+int b200_subsample2(const void* x, void* y, int N, int H, int W, int C, b200_stream_t stream);
+/* dx[n,2h,2w,c] += g[n,h,w,c] for c < Cg (backward of subsample (+ zero channel pad)); dx is
+ * [N,2H,2W,C] with C >= Cg, g is [N,H,W,Cg]. */
+int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg,
+                      b200_stream_t stream);
+
+/* ---- pooling (resnet.py:77-87) ------------------------------------------------------------- */
+int b200_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad,
+                     b200_stream_t stream);
+int b200_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int k, int stride, int pad,
+                     b200_stream_t stream);
+int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad,
+                     b200_stream_t stream);
+int b200_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W,
+                     int C, int k, int stride, int pad, b200_stream_t stream);
+
+/* ---- classifier head (resnet.py:117-120; metrics.py:10-29) ---------------------------------- */
+/* logits[B,O] (bf16) = bf16(x[B,I] (bf16) . bf16(w[O,I])^T + bf16(b[O])) */
+int b200_linear_fwd(const void* x, const float* w, const float* b, void* logits, int B, int I, int O,
+                    b200_stream_t stream);
+/* dx (bf16 [B,I]), dw (fp32 [O,I]), db (fp32 [O]) from dlogits (bf16 [B,O]) */
+int b200_linear_bwd(const void* dlogits, const void* x, const float* w, void* dx, float* dw,
+                    float* db, int B, int I, int O, b200_stream_t stream);
+/* Mean cross entropy over the batch + top-1 / top-5 error. out (fp32[3], may be NULL) =
+ * {loss, top1_err, top5_err}; dlogits (bf16 [B,O], may be NULL) = (softmax - onehot) * s / B with
+ * s = *grad_scale (device fp32 scalar, NULL => 1). labels int64. */
+int b200_ce_topk(const void* logits, const int64_t* labels, float* out, void* dlogits,
+                 const float* grad_scale, int B, int O, b200_stream_t stream);
+
+/* ---- optimizer (torch.optim.SGD via optim_util.py:11-18, stepped at training.py:108-113) ------
+ * One launch for `n` tensors. Per element: g = grad (* inv_scale); g += wd * p;
+ * buf = first_step ? g : momentum*buf + (1-dampening)*g; g = nesterov ? g + momentum*buf : buf;
+ * p -= lr * g. If found_inf != NULL and *found_inf != 0 the step is skipped (GradScaler contract).
+ * params/grads/bufs: device arrays of n device pointers; sizes: device array of n element counts. */
+int b200_sgd_step(float* const* params, const float* const* grads, float* const* bufs,
+                  const int64_t* sizes, int n, int64_t max_size, float lr, float momentum,
+                  float dampening, float weight_decay, int nesterov, int first_step,
+                  const float* inv_scale, const float* found_inf, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RESNET_H_ */

@@ -1,0 +1,795 @@
+// libb200resnet.so — extern "C" entry points declared in include/b200resnet.h.
+// Host-side planning (tile shapes, tap tables, TMA descriptors, split factors) + kernel launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/b200resnet.h"
+#include "common.cuh"
+#include "conv_direct.cuh"
+#include "conv_tc.cuh"
+#include "elementwise.cuh"
+#include "head_sgd.cuh"
+
+using namespace b200;
+
+// -------------------------------------------------------------------------------------------------
+// error handling
+// -------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define B200_REQUIRE(cond, ...) \
+  do {                          \
+    if (!(cond)) return fail(1, __VA_ARGS__); \
+  } while (0)
+
+#define B200_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) return fail(2, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                                          \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) return fail(3, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+static inline int ew_grid(size_t work_items, int per_block = EW_THREADS) {
+  size_t b = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)num_sms() * 16;
+  return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+extern "C" int b200_version(void) { return 100; }
+extern "C" const char* b200_last_error(void) { return g_err; }
+
+extern "C" int b200_device_check(void) {
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  B200_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B200_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  B200_REQUIRE(major == 10, "device is sm_%d%d; this library only carries sm_100a code", major, minor);
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point resolved at run time: no link-time libcuda dependency)
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int inner_elems) {
+  return inner_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : inner_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// bf16 tensor [N][H][W][C] with box (bc, bw, bh, bn)
+static int make_tmap_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bc,
+                          int bw, int bh, int bn) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled(4d) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d,%d)", (int)r,
+               N, H, W, C, bc, bw, bh, bn);
+  return 0;
+}
+
+// bf16 matrix [rows][cols] (cols contiguous) with box (bc cols, br rows)
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int bc, int br) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)br};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (rows=%d cols=%d box=%d,%d)",
+               (int)r, rows, cols, bc, br);
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv planning
+// -------------------------------------------------------------------------------------------------
+struct TilePlan {
+  int bw, bh, bn, rows_valid, tiles_w, tiles_h, tiles_n;
+};
+
+static int largest_divisor_leq(int n, int cap) {
+  for (int d = std::min(n, cap); d >= 1; --d)
+    if (n % d == 0) return d;
+  return 1;
+}
+
+// Box of output pixels (w, h, images) with at most 128 pixels.
+static TilePlan plan_tiles(int Nimg, int P, int Q) {
+  TilePlan t;
+  if (Q >= 128) {
+    t.bw = 128; t.bh = 1; t.bn = 1;
+  } else {
+    t.bw = Q;
+    const int mh = 128 / Q;
+    if (mh >= P) {
+      t.bh = P;
+      t.bn = largest_divisor_leq(Nimg, std::max(1, 128 / (Q * P)));
+    } else {
+      int d = largest_divisor_leq(P, mh);
+      t.bh = (2 * d > mh) ? d : mh;
+      t.bn = 1;
+    }
+  }
+  t.rows_valid = t.bw * t.bh * t.bn;
+  t.tiles_w = (Q + t.bw - 1) / t.bw;
+  t.tiles_h = (P + t.bh - 1) / t.bh;
+  t.tiles_n = (Nimg + t.bn - 1) / t.bn;
+  return t;
+}
+
+static int pick_kc(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16; }
+
+// largest divisor of K that is a multiple of `mult` and <= cap (0 if none)
+static int pick_bn(int K, int mult, int cap) {
+  for (int bn = std::min(K, cap) / mult * mult; bn >= mult; bn -= mult)
+    if (K % bn == 0) return bn;
+  return 0;
+}
+
+static inline int floordiv2(int e) { return (e >= 0) ? e / 2 : -((-e + 1) / 2); }
+static inline int mod2(int e) { return ((e % 2) + 2) % 2; }
+
+static bool same_geometry(int H, int W, int R, int S, int stride, int pad, int* P, int* Q) {
+  *P = (H + 2 * pad - R) / stride + 1;
+  *Q = (W + 2 * pad - S) / stride + 1;
+  if (stride == 1) return *P == H && *Q == W;
+  if (stride == 2) return (H % 2 == 0) && (W % 2 == 0) && *P == H / 2 && *Q == W / 2;
+  return false;
+}
+
+extern "C" int b200_conv2d_tc_supported(int pass, int N, int H, int W, int C, int K, int R, int S,
+                                        int stride, int pad) {
+  int P, Q;
+  if (N < 1 || R * S > TC_MAX_TAPS) return 0;
+  if (!same_geometry(H, W, R, S, stride, pad, &P, &Q)) return 0;
+  if (C % 16 != 0 || K % 16 != 0) return 0;
+  if (pass == B200_PASS_WGRAD) {
+    TilePlan t = plan_tiles(N, P, Q);
+    if (t.rows_valid % 16 != 0) return 0;
+  }
+  return 1;
+}
+
+extern "C" size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int C, int K, int R,
+                                              int S, int stride, int pad, int algo) {
+  if (algo == B200_ALGO_DIRECT) return 0;
+  if (stride != 2) return 0;
+  if (!b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad)) return 0;
+  return (size_t)N * H * W * C * 2;  // parity-split copy of the full-resolution tensor
+}
+
+static bool use_tc(int algo, int pass, int N, int H, int W, int C, int K, int R, int S, int stride,
+                   int pad) {
+  if (algo == B200_ALGO_DIRECT) return false;
+  return b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad) != 0;
+}
+
+template <int KC>
+static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  const int max_dyn = 228352;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_dyn));
+    attr_set = true;
+  }
+  a.a_bytes = 128u * KC * 2u;
+  const uint32_t b_bytes = ((uint32_t)a.BN * KC * 2u + 1023u) & ~1023u;
+  a.stage_bytes = a.a_bytes + b_bytes;
+  a.stages = std::min<int>(TC_MAX_STAGES, (max_dyn - 1024) / (int)a.stage_bytes);
+  B200_REQUIRE(a.stages >= 2, "conv_tc: tile does not fit in shared memory");
+  a.tx_bytes = (uint32_t)a.rows_valid * KC * 2u + (uint32_t)a.BN * KC * 2u;
+  size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
+  dyn = std::max<size_t>(dyn, 120 * 1024);  // one CTA per SM: the CTA owns all 512 TMEM columns
+  const int grid = std::min(a.num_tiles, num_sms());
+  conv_tc_kernel<KC><<<grid, TC_THREADS, dyn, st>>>(tmA, tmB, a);
+  B200_LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
+// One shifted-window GEMM launch. act: [Nact][Ha][Wa][Cin] (bf16), wmat: [Cout][ntaps*Cin] (bf16),
+// out: [Nimg][P][Q][Cout].
+static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
+                       int wcols, const TapTable& taps, void* out, const void* residual,
+                       const float* bias, int Nimg, int P, int Q, cudaStream_t st) {
+  const int KC = pick_kc(Cin);
+  const int BN = pick_bn(Cout, 16, 256);
+  B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
+  TilePlan t = plan_tiles(Nimg, P, Q);
+  ConvTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bw = t.bw; a.bh = t.bh; a.bn = t.bn; a.rows_valid = t.rows_valid;
+  a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
+  a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = Cin / KC;
+  a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
+  a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles;
+  a.taps = taps;
+  a.out = reinterpret_cast<bf16*>(out);
+  a.residual = reinterpret_cast<const bf16*>(residual);
+  a.bias = bias;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
+  if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN)) return rc;
+  switch (KC) {
+    case 64: return launch_conv_tc<64>(tmA, tmB, a, st);
+    case 32: return launch_conv_tc<32>(tmA, tmB, a, st);
+    default: return launch_conv_tc<16>(tmA, tmB, a, st);
+  }
+}
+
+// taps of fprop / wgrad (window displacement on the input, column in the KRSC filter matrix)
+static TapTable fprop_taps(int N, int C, int R, int S, int stride, int pad) {
+  TapTable tt;
+  memset(&tt, 0, sizeof(tt));
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      const int i = tt.n++;
+      const int eh = r - pad, ew = s - pad;
+      if (stride == 1) {
+        tt.dh[i] = eh; tt.dw[i] = ew; tt.dn[i] = 0;
+      } else {
+        tt.dh[i] = floordiv2(eh); tt.dw[i] = floordiv2(ew);
+        tt.dn[i] = (mod2(eh) * 2 + mod2(ew)) * N;
+      }
+      tt.wcol[i] = (r * S + s) * C;
+    }
+  return tt;
+}
+
+extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
+                                 const void* residual, void* y, int N, int H, int W, int C, int K,
+                                 int R, int S, int stride, int pad, int algo, void* ws,
+                                 size_t ws_bytes, b200_stream_t stream) {
+  B200_REQUIRE(x && w_krsc && y, "conv2d_fprop: null pointer");
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d unsupported", stride);
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  B200_REQUIRE(P > 0 && Q > 0, "conv2d_fprop: empty output");
+  cudaStream_t st = as_stream(stream);
+  const bool tc = use_tc(algo, B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad);
+  B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
+  if (!tc) {
+    ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
+    const size_t total = (size_t)N * P * Q * K;
+    conv_fprop_direct_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(
+        (const bf16*)x, (const bf16*)w_krsc, bias, (const bf16*)residual, (bf16*)y, d);
+    B200_LAUNCH_CHECK("conv_fprop_direct_kernel");
+    return 0;
+  }
+  const void* act = x;
+  int Nact = N, Ha = H, Wa = W;
+  if (stride == 2) {
+    const size_t need = (size_t)N * H * W * C * 2;
+    B200_REQUIRE(ws && ws_bytes >= need, "conv2d_fprop: workspace too small (%zu < %zu)", ws_bytes,
+                 need);
+    parity_kernel<false><<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
+        (const bf16*)x, (bf16*)ws, N, H, W, C);
+    B200_LAUNCH_CHECK("parity_kernel<split>");
+    act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
+  }
+  TapTable tt = fprop_taps(N, C, R, S, stride, pad);
+  return run_conv_tc(act, Nact, Ha, Wa, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st);
+}
+
+// merge of the parity-split dx with an optional addend
+__global__ void parity_merge_add_kernel(const bf16* __restrict__ src, const bf16* __restrict__ addend,
+                                        bf16* __restrict__ dst, int N, int H, int W, int C) {
+  const int CG = C / 8;
+  const size_t nvec = (size_t)N * H * W * CG;
+  const int H2 = H / 2, W2 = W / 2;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    const int ph = (h & 1) * 2 + (w & 1);
+    const size_t ppix = (((size_t)ph * N + n) * H2 + (h >> 1)) * W2 + (w >> 1);
+    Vec8 a;
+    a.raw = ldg_stream(src + ppix * C + (size_t)cg * 8);
+    if (addend) {
+      Vec8 b;
+      b.raw = ldg_stream(addend + v * 8);
+      float fa[8], fb[8];
+      a.to_float(fa);
+      b.to_float(fb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fa[j] = round_bf16(fa[j] + fb[j]);
+      a.from_float(fa);
+    }
+    stg_stream(dst + v * 8, a.raw);
+  }
+}
+
+extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx,
+                                 int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                                 int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+  B200_REQUIRE(dy && w_crsk && dx, "conv2d_dgrad: null pointer");
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d unsupported", stride);
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = as_stream(stream);
+  const bool tc = use_tc(algo, B200_PASS_DGRAD, N, H, W, C, K, R, S, stride, pad);
+  B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_dgrad: shape not supported by the tcgen05 path");
+  if (!tc) {
+    ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
+    const size_t total = (size_t)N * H * W * C;
+    conv_dgrad_direct_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(
+        (const bf16*)dy, (const bf16*)w_crsk, (const bf16*)addend, (bf16*)dx, d);
+    B200_LAUNCH_CHECK("conv_dgrad_direct_kernel");
+    return 0;
+  }
+  if (stride == 1) {
+    // dx[h,w] = sum_{r,s} dy[h + pad - r, w + pad - s] . W[:, r, s, :]
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        const int i = tt.n++;
+        tt.dh[i] = pad - r; tt.dw[i] = pad - s; tt.dn[i] = 0;
+        tt.wcol[i] = (r * S + s) * K;
+      }
+    return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dx, addend, nullptr, N, H, W, st);
+  }
+  // stride 2: one launch per output parity phase (a, b), into the parity-split workspace
+  const size_t need = (size_t)N * H * W * C * 2;
+  B200_REQUIRE(ws && ws_bytes >= need, "conv2d_dgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  const int H2 = H / 2, W2 = W / 2;
+  const size_t phase_elems = (size_t)N * H2 * W2 * C;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      TapTable tt;
+      memset(&tt, 0, sizeof(tt));
+      for (int r = 0; r < R; ++r) {
+        if (mod2(a + pad - r) != 0) continue;
+        for (int s = 0; s < S; ++s) {
+          if (mod2(b + pad - s) != 0) continue;
+          const int i = tt.n++;
+          tt.dh[i] = floordiv2(a + pad - r); tt.dw[i] = floordiv2(b + pad - s); tt.dn[i] = 0;
+          tt.wcol[i] = (r * S + s) * K;
+        }
+      }
+      bf16* dst = reinterpret_cast<bf16*>(ws) + (size_t)(a * 2 + b) * phase_elems;
+      if (tt.n == 0) {
+        B200_CUDA(cudaMemsetAsync(dst, 0, phase_elems * 2, st));
+        continue;
+      }
+      if (int rc = run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dst, nullptr, nullptr, N, H2,
+                               W2, st))
+        return rc;
+    }
+  parity_merge_add_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
+      (const bf16*)ws, (const bf16*)addend, (bf16*)dx, N, H, W, C);
+  B200_LAUNCH_CHECK("parity_merge_add_kernel");
+  return 0;
+}
+
+template <int SL>
+static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, WgradTcArgs& a,
+                           cudaStream_t st) {
+  static bool attr_set = false;
+  const int max_dyn = 228352;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_dyn));
+    attr_set = true;
+  }
+  a.slab_bytes = 128u * SL * 2u;
+  a.stage_bytes = (uint32_t)(128 / SL + a.BN / SL) * a.slab_bytes;
+  a.stages = std::min<int>(4, (max_dyn - 1024) / (int)a.stage_bytes);
+  B200_REQUIRE(a.stages >= 2, "wgrad_tc: tile does not fit in shared memory");
+  size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
+  dyn = std::max<size_t>(dyn, 120 * 1024);
+  dim3 grid(a.n_mtiles * a.n_ntiles, a.splits);
+  wgrad_tc_kernel<SL><<<grid, TC_THREADS, dyn, st>>>(tmX, tmDy, a);
+  B200_LAUNCH_CHECK("wgrad_tc_kernel");
+  return 0;
+}
+
+extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N,
+                                 int H, int W, int C, int K, int R, int S, int stride, int pad,
+                                 int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+  B200_REQUIRE(dy && x && dw_krsc, "conv2d_wgrad: null pointer");
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d unsupported", stride);
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = as_stream(stream);
+  const size_t npix = (size_t)N * P * Q;
+  if (dbias) {
+    B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
+    const int ppc = 512;
+    conv_dbias_kernel<<<(unsigned)((npix + ppc - 1) / ppc), 256, 0, st>>>((const bf16*)dy, dbias, npix,
+                                                                          K, ppc);
+    B200_LAUNCH_CHECK("conv_dbias_kernel");
+  }
+  const bool tc = use_tc(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);
+  B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_wgrad: shape not supported by the tcgen05 path");
+  if (!tc) {
+    ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
+    const int total = K * R * S * C;
+    const int bx = (total + 255) / 256;
+    int chunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_sms() * 8 / bx + 1, npix / 64 + 1));
+    const int ppc = (int)((npix + chunks - 1) / chunks);
+    chunks = (int)((npix + ppc - 1) / ppc);
+    if (chunks > 1) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)total * 4, st));
+    conv_wgrad_direct_kernel<<<dim3(bx, chunks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x,
+                                                               dw_krsc, d, ppc);
+    B200_LAUNCH_CHECK("conv_wgrad_direct_kernel");
+    return 0;
+  }
+  const void* act = x;
+  int Nact = N, Ha = H, Wa = W;
+  if (stride == 2) {
+    const size_t need = (size_t)N * H * W * C * 2;
+    B200_REQUIRE(ws && ws_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)", ws_bytes,
+                 need);
+    parity_kernel<false><<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
+        (const bf16*)x, (bf16*)ws, N, H, W, C);
+    B200_LAUNCH_CHECK("parity_kernel<split>");
+    act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
+  }
+  const int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
+  int BN = pick_bn(K, SL, 160);
+  B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
+  TilePlan t = plan_tiles(N, P, Q);
+  WgradTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bw = t.bw; a.bh = t.bh; a.bn = t.bn;
+  a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
+  a.num_ptiles = t.tiles_w * t.tiles_h * t.tiles_n;
+  a.kmmas = t.rows_valid / 16;
+  a.slabs_per_tap = C / SL;
+  a.nslabs_total = R * S * a.slabs_per_tap;
+  const int spm = 128 / SL;
+  a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
+  a.BN = BN; a.n_ntiles = K / BN;
+  a.ktot = R * S * C;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < BN) a.tmem_cols *= 2;
+  const int cols = a.n_mtiles * a.n_ntiles;
+  int splits = std::max(1, (2 * num_sms() + cols - 1) / cols);
+  splits = std::min(splits, a.num_ptiles);
+  const int per = (a.num_ptiles + splits - 1) / splits;
+  a.splits = (a.num_ptiles + per - 1) / per;
+  a.taps = fprop_taps(N, C, R, S, stride, pad);
+  a.dw = dw_krsc;
+  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)K * a.ktot * 4, st));
+  CUtensorMap tmX, tmDy;
+  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn)) return rc;
+  if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
+  if (SL == 32) return launch_wgrad_tc<32>(tmX, tmDy, a, st);
+  return launch_wgrad_tc<16>(tmX, tmDy, a, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// layout / filters
+// -------------------------------------------------------------------------------------------------
+extern "C" int b200_weight_prep(const float* w_krsc, void* w_krsc_bf16, void* w_crsk_bf16, int K,
+                                int RS, int C, b200_stream_t stream) {
+  B200_REQUIRE(w_krsc, "weight_prep: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const size_t n = (size_t)K * RS * C;
+  if (w_krsc_bf16) {
+    weight_cast_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(w_krsc, (bf16*)w_krsc_bf16, n);
+    B200_LAUNCH_CHECK("weight_cast_kernel");
+  }
+  if (w_crsk_bf16) {
+    dim3 grid((C + 31) / 32, (K + 31) / 32, RS);
+    weight_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(w_krsc, (bf16*)w_crsk_bf16, K, RS, C);
+    B200_LAUNCH_CHECK("weight_transpose_kernel");
+  }
+  return 0;
+}
+
+extern "C" int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,
+                                          b200_stream_t stream) {
+  B200_REQUIRE(x && y, "nchw_f32_to_nhwc_bf16: null pointer");
+  nchw_f32_to_nhwc_bf16_kernel<<<ew_grid((size_t)N * H * W), EW_THREADS, 0, as_stream(stream)>>>(
+      x, (bf16*)y, N, C, H, W);
+  B200_LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// batch norm family
+// -------------------------------------------------------------------------------------------------
+static int bn_blocks(int64_t rows, int C) {
+  const int CG = C / 8;
+  const int CGb = std::min(EW_THREADS, CG);
+  const int RP = EW_THREADS / CGb;
+  int64_t b = (rows + (int64_t)RP * 8 - 1) / ((int64_t)RP * 8);
+  b = std::min<int64_t>(b, std::min(BN_MAX_BLOCKS, num_sms() * 4));
+  return (int)std::max<int64_t>(1, b);
+}
+
+extern "C" size_t b200_bn_workspace_bytes(int64_t rows, int C) {
+  (void)rows;
+  return (size_t)BN_MAX_BLOCKS * 2 * C * sizeof(float);
+}
+
+extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum,
+                             float* mean, float* invstd, float* running_mean, float* running_var,
+                             int64_t* num_batches_tracked, void* ws, size_t ws_bytes,
+                             b200_stream_t stream) {
+  B200_REQUIRE(x && mean && invstd && ws, "bn_stats: null pointer");
+  B200_REQUIRE(C % 8 == 0, "bn_stats: C=%d must be a multiple of 8", C);
+  B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_stats: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int nblk = bn_blocks(rows, C);
+  const int CG = C / 8;
+  dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
+  bn_stats_partial_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(
+      (const bf16*)x, rows, C, (float*)ws);
+  B200_LAUNCH_CHECK("bn_stats_partial_kernel");
+  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, nblk, rows, C, eps,
+                                                            momentum, mean, invstd, running_mean,
+                                                            running_var, num_batches_tracked);
+  B200_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  return 0;
+}
+
+static uint32_t drop_threshold(float p) {
+  if (p <= 0.f) return 0;
+  double t = (double)p * 65536.0 + 0.5;
+  if (t > 65535.0) t = 65535.0;
+  return (uint32_t)t;
+}
+
+extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const float* mean,
+                               const float* invstd, int stat_is_var, float eps, const float* gamma,
+                               const float* beta, const void* skip, int skip_mode, int skip_C,
+                               int relu, float dropout_p, uint64_t seed, b200_stream_t stream) {
+  B200_REQUIRE(x && y, "bn_act_fwd: null pointer");
+  B200_REQUIRE(C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
+  B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "bn_act_fwd: dropout_p out of range");
+  B200_REQUIRE(skip_mode == B200_SKIP_NONE || skip, "bn_act_fwd: skip_mode set without skip tensor");
+  B200_REQUIRE(skip_mode != B200_SKIP_SUBSAMPLE_PAD || (skip_C % 8 == 0 && skip_C <= C),
+               "bn_act_fwd: bad skip_C=%d", skip_C);
+  BnActFwdArgs a;
+  a.x = (const bf16*)x; a.y = (bf16*)y; a.skip = (const bf16*)skip;
+  a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta;
+  a.N = N; a.H = H; a.W = W; a.C = C;
+  a.skip_mode = skip ? skip_mode : 0; a.skip_C = skip_C;
+  a.stat_is_var = stat_is_var; a.relu = relu;
+  a.affine = (gamma && beta && mean && invstd) ? 1 : 0;
+  a.eps = eps;
+  a.inv_keep = 1.f / (1.f - dropout_p);
+  a.drop_thr = drop_threshold(dropout_p);
+  a.seed = seed;
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(bn_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   200 * 1024));
+    attr_set = true;
+  }
+  const size_t nvec = (size_t)N * H * W * C / 8;
+  bn_act_fwd_kernel<<<ew_grid(nvec), EW_THREADS, smem, as_stream(stream)>>>(a);
+  B200_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
+                               const void* addend, int64_t rows, int C, const float* mean,
+                               const float* invstd, const float* gamma, float* dgamma, float* dbeta,
+                               int relu, float dropout_p, uint64_t seed, void* ws, size_t ws_bytes,
+                               b200_stream_t stream) {
+  B200_REQUIRE(dy && dx, "bn_act_bwd: null pointer");
+  B200_REQUIRE(C % 8 == 0, "bn_act_bwd: C=%d must be a multiple of 8", C);
+  B200_REQUIRE(!relu || y, "bn_act_bwd: relu mask needs the forward output y");
+  cudaStream_t st = as_stream(stream);
+  BnActBwdArgs a;
+  a.dy = (const bf16*)dy; a.y = (const bf16*)y; a.x = (const bf16*)x;
+  a.dx = (bf16*)dx; a.dskip = (bf16*)dskip; a.addend = (const bf16*)addend;
+  a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.rows = rows; a.C = C; a.relu = relu;
+  a.affine = (gamma && mean && invstd) ? 1 : 0;
+  a.inv_keep = 1.f / (1.f - dropout_p);
+  a.drop_thr = drop_threshold(dropout_p);
+  a.seed = seed;
+  if (a.affine) {
+    B200_REQUIRE(x && dgamma && dbeta && ws, "bn_act_bwd: null pointer (affine path)");
+    B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_act_bwd: workspace too small");
+    const int nblk = bn_blocks(rows, C);
+    const int CG = C / 8;
+    dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
+    bn_act_bwd_reduce_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(a, (float*)ws);
+    B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
+    B200_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  }
+  const size_t smem = a.affine ? (size_t)5 * C * sizeof(float) : 0;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(bn_act_bwd_apply_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const size_t nvec = (size_t)rows * C / 8;
+  bn_act_bwd_apply_kernel<<<ew_grid(nvec), EW_THREADS, smem, st>>>(a);
+  B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int b200_subsample2(const void* x, void* y, int N, int H, int W, int C,
+                               b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 8 == 0, "subsample2: bad arguments");
+  subsample2_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)x, (bf16*)y, N, H, W, C);
+  B200_LAUNCH_CHECK("subsample2_kernel");
+  return 0;
+}
+
+extern "C" int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg,
+                                 b200_stream_t stream) {
+  B200_REQUIRE(dx && g && C % 8 == 0 && Cg % 8 == 0 && Cg <= C, "upsample_add: bad arguments");
+  upsample_add_kernel<<<ew_grid((size_t)N * H * W * Cg / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (bf16*)dx, (const bf16*)g, N, H, W, C, Cg);
+  B200_LAUNCH_CHECK("upsample_add_kernel");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// pooling
+// -------------------------------------------------------------------------------------------------
+static PoolDims pool_dims(int N, int H, int W, int C, int k, int stride, int pad) {
+  PoolDims d{N, H, W, C, k, stride, pad, (H + 2 * pad - k) / stride + 1, (W + 2 * pad - k) / stride + 1};
+  return d;
+}
+
+extern "C" int b200_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride,
+                                int pad, b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "avgpool_fwd: bad arguments");
+  PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  avgpool_fwd_kernel<<<ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)x, (bf16*)y, d);
+  B200_LAUNCH_CHECK("avgpool_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int k,
+                                int stride, int pad, b200_stream_t stream) {
+  B200_REQUIRE(dy && dx && C % 8 == 0 && stride >= 1, "avgpool_bwd: bad arguments");
+  PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  avgpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)dy, (bf16*)dx, d);
+  B200_LAUNCH_CHECK("avgpool_bwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride,
+                                int pad, b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "maxpool_fwd: bad arguments");
+  PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  maxpool_fwd_kernel<<<ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)x, (bf16*)y, d);
+  B200_LAUNCH_CHECK("maxpool_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H,
+                                int W, int C, int k, int stride, int pad, b200_stream_t stream) {
+  (void)y;
+  B200_REQUIRE(dy && x && dx && stride >= 1, "maxpool_bwd: bad arguments");
+  PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  maxpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)dy, (const bf16*)x, (bf16*)dx, d);
+  B200_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// head
+// -------------------------------------------------------------------------------------------------
+extern "C" int b200_linear_fwd(const void* x, const float* w, const float* b, void* logits, int B,
+                               int I, int O, b200_stream_t stream) {
+  B200_REQUIRE(x && w && logits, "linear_fwd: null pointer");
+  const size_t threads = (size_t)B * O * 32;
+  linear_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>((const bf16*)x, w, b,
+                                                                              (bf16*)logits, B, I, O);
+  B200_LAUNCH_CHECK("linear_fwd_kernel");
+  return 0;
+}
+
+extern "C" int b200_linear_bwd(const void* dlogits, const void* x, const float* w, void* dx,
+                               float* dw, float* db, int B, int I, int O, b200_stream_t stream) {
+  B200_REQUIRE(dlogits && x && w, "linear_bwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (dx) {
+    linear_bwd_dx_kernel<<<(unsigned)(((size_t)B * I + 255) / 256), 256, 0, st>>>(
+        (const bf16*)dlogits, w, (bf16*)dx, B, I, O);
+    B200_LAUNCH_CHECK("linear_bwd_dx_kernel");
+  }
+  if (dw) {
+    linear_bwd_dw_kernel<<<(unsigned)(((size_t)O * I + 255) / 256), 256, 0, st>>>(
+        (const bf16*)dlogits, (const bf16*)x, dw, db, B, I, O);
+    B200_LAUNCH_CHECK("linear_bwd_dw_kernel");
+  }
+  return 0;
+}
+
+extern "C" int b200_ce_topk(const void* logits, const int64_t* labels, float* out, void* dlogits,
+                            const float* grad_scale, int B, int O, b200_stream_t stream) {
+  B200_REQUIRE(logits && labels, "ce_topk: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (out) B200_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
+  const size_t threads = (size_t)B * 32;
+  ce_topk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+      (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
+  B200_LAUNCH_CHECK("ce_topk_kernel");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// optimizer
+// -------------------------------------------------------------------------------------------------
+extern "C" int b200_sgd_step(float* const* params, const float* const* grads, float* const* bufs,
+                             const int64_t* sizes, int n, int64_t max_size, float lr, float momentum,
+                             float dampening, float weight_decay, int nesterov, int first_step,
+                             const float* inv_scale, const float* found_inf, b200_stream_t stream) {
+  B200_REQUIRE(params && grads && bufs && sizes && n > 0, "sgd_step: bad arguments");
+  SgdArgs a{params, grads, bufs, sizes, lr, momentum, dampening, weight_decay,
+            nesterov, first_step, inv_scale, found_inf};
+  const int64_t chunk = (int64_t)SGD_THREADS * SGD_VEC_PER_THREAD * 4;
+  dim3 grid((unsigned)((max_size + chunk - 1) / chunk), n);
+  sgd_step_kernel<<<grid, SGD_THREADS, 0, as_stream(stream)>>>(a);
+  B200_LAUNCH_CHECK("sgd_step_kernel");
+  return 0;
+}

@@ -1,0 +1,406 @@
+// tcgen05 implicit-GEMM convolution kernels for sm_100a.
+//
+// Both kernels see a convolution as a sum over filter taps of "shifted-window" GEMMs: for tap t the
+// activation operand is the NHWC tensor read through a 4-D TMA box displaced by (dh, dw) pixels
+// (out-of-bounds pixels are zero-filled by the TMA unit, which implements the zero padding), so no
+// im2col buffer ever exists. Stride-2 convolutions read a parity-split copy of the input
+// ([4 phases][N][H/2][W/2][C]) through the same mechanism: every tap maps to one phase image
+// and a unit-stride displacement inside it.
+//
+//   conv_tc_kernel   : D[pixel][k] = sum_t sum_c A_t[pixel][c] * B[k][t,c]       (fprop and dgrad)
+//                      A, B K-major in shared memory (channels contiguous), 128-pixel M tile,
+//                      N tile = BN output channels, accumulators double-buffered in TMEM,
+//                      warp-specialised: TMA producer / MMA issuer / 4 epilogue warps, persistent.
+//   wgrad_tc_kernel  : D[(t,c)][k] = sum_pixel X_t[pixel][c] * dY[pixel][k]      (wgrad)
+//                      both operands MN-major (the reduction runs over pixels, the slow axis of NHWC),
+//                      M tile = 128 rows made of 128/SL channel slabs of any (tap, channel-chunk),
+//                      split over pixel ranges with fp32 reduction in global memory.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int TC_MAX_TAPS = 9;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+
+struct TapTable {
+  int n;
+  int dh[TC_MAX_TAPS];    // pixel displacement of the window (rows)
+  int dw[TC_MAX_TAPS];    // pixel displacement of the window (cols)
+  int dn[TC_MAX_TAPS];    // image-index displacement (selects the parity phase image)
+  int wcol[TC_MAX_TAPS];  // first column of this tap inside the filter matrix
+};
+
+struct ConvTcArgs {
+  int bw, bh, bn;                   // TMA box in pixels (w, h, images); bw*bh*bn <= 128
+  int rows_valid;                   // bw*bh*bn
+  int tiles_w, tiles_h, tiles_n;    // pixel tiles per dimension
+  int n_ntiles;                     // output-channel tiles
+  int BN;                           // output channels per tile (UMMA N)
+  int nkc;                          // Cin / KC
+  int P, Q, Nimg;                   // output extent
+  int ldo;                          // output channel pitch (elements)
+  int num_tiles;
+  int stages;
+  uint32_t stage_bytes;
+  uint32_t a_bytes;                 // 128 * KC * 2
+  uint32_t tx_bytes;                // bytes landed per stage
+  TapTable taps;
+  bf16* out;
+  const bf16* residual;
+  const float* bias;
+};
+
+template <int KC>
+struct KMajorCfg {
+  static constexpr uint32_t ROW_BYTES = KC * 2;
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;
+  static constexpr uint32_t LAYOUT = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvTcArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4);
+    mbar_init(&tempty_bar[1], 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int tiles_hw = args.tiles_w * args.tiles_h;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        const int nt = tile % args.n_ntiles;
+        const int mt = tile / args.n_ntiles;
+        const int w0 = (mt % args.tiles_w) * args.bw;
+        const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
+        const int n0 = (mt / tiles_hw) * args.bn;
+        for (int t = 0; t < args.taps.n; ++t) {
+          const int cw = w0 + args.taps.dw[t];
+          const int ch = h0 + args.taps.dh[t];
+          const int cn = n0 + args.taps.dn[t];
+          const int wc = args.taps.wcol[t];
+          for (int kc = 0; kc < args.nkc; ++kc) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
+            uint8_t* b_dst = a_dst + args.a_bytes;
+            mbar_expect_tx(&full_bar[s], args.tx_bytes);
+            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw, ch, cn);
+            tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
+            if (++s == args.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc_bf16(128, args.BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      const int nk = args.taps.n * args.nkc;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * args.stage_bytes);
+          const uint32_t b_addr = a_addr + args.a_bytes;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, KMajorCfg<KC>::SBO,
+                                               KMajorCfg<KC>::LAYOUT);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, KMajorCfg<KC>::SBO,
+                                               KMajorCfg<KC>::LAYOUT);
+            umma_bf16_ss(d_addr, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == args.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const int wi = m % args.bw;
+    const int hi = (m / args.bw) % args.bh;
+    const int ni = m / (args.bw * args.bh);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const int nt = tile % args.n_ntiles;
+      const int mt = tile / args.n_ntiles;
+      const int w = (mt % args.tiles_w) * args.bw + wi;
+      const int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
+      const int n = (mt / tiles_hw) * args.bn + ni;
+      const bool valid = (m < args.rows_valid) && (w < args.Q) && (h < args.P) && (n < args.Nimg);
+      const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
+      const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
+      bf16* orow = args.out + off;
+      const bf16* rrow = args.residual ? args.residual + off : nullptr;
+      const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
+      for (int c = 0; c < args.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (brow) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
+          }
+          if (rrow) {
+            Vec8 r0, r1;
+            r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
+            r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
+            float rf[16];
+            r0.to_float(rf);
+            r1.to_float(rf + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+          }
+          Vec8 o0, o1;
+          o0.from_float(f);
+          o1.from_float(f + 8);
+          *reinterpret_cast<uint4*>(orow + c) = o0.raw;
+          *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// wgrad
+// -------------------------------------------------------------------------------------------------
+struct WgradTcArgs {
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n;
+  int num_ptiles;        // pixel tiles in total
+  int kmmas;             // 16-pixel MMAs per pixel tile (rows_valid / 16)
+  int nslabs_total;      // ntaps * (Cin / SL)
+  int slabs_per_tap;     // Cin / SL
+  int n_mtiles;          // ceil(nslabs_total / (128 / SL))
+  int n_ntiles;          // Cout / BN
+  int BN;
+  int splits;            // pixel-range splits (gridDim.y)
+  int ktot;              // ntaps * Cin: row pitch of dw
+  int stages;
+  int tmem_cols;
+  uint32_t stage_bytes;
+  uint32_t slab_bytes;   // 128 * SL * 2
+  TapTable taps;
+  float* dw;
+};
+
+template <int SL>
+struct MnMajorCfg {
+  static constexpr uint32_t ROW_BYTES = SL * 2;
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;              // next group of 8 pixels
+  static constexpr uint32_t LBO = 128 * ROW_BYTES;            // next channel slab
+  static constexpr uint32_t LAYOUT = (SL == 64) ? 2u : (SL == 32) ? 4u : 6u;
+  static constexpr int SLABS_PER_MTILE = 128 / SL;
+};
+
+template <int SL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                const __grid_constant__ WgradTcArgs args) {
+  using Cfg = MnMajorCfg<SL>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ uint64_t tfull_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, (uint32_t)args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int mt = blockIdx.x % args.n_mtiles;
+  const int nt = blockIdx.x / args.n_mtiles;
+  const int per = (args.num_ptiles + args.splits - 1) / args.splits;
+  const int pt0 = blockIdx.y * per;
+  const int pt1 = min(args.num_ptiles, pt0 + per);
+  const int tiles_hw = args.tiles_w * args.tiles_h;
+  const int q0 = mt * Cfg::SLABS_PER_MTILE;
+  const int na = min(Cfg::SLABS_PER_MTILE, args.nslabs_total - q0);  // valid A slabs
+  const int nb = args.BN / SL;                                        // B slabs
+  const uint32_t b_off = Cfg::SLABS_PER_MTILE * args.slab_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t tx = (uint32_t)(na + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        const int w0 = (pt % args.tiles_w) * args.bw;
+        const int h0 = ((pt / args.tiles_w) % args.tiles_h) * args.bh;
+        const int n0 = (pt / tiles_hw) * args.bn;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
+        uint8_t* b_dst = a_dst + b_off;
+        mbar_expect_tx(&full_bar[s], tx);
+        for (int i = 0; i < na; ++i) {
+          const int q = q0 + i;
+          const int t = q / args.slabs_per_tap;
+          const int ck = q % args.slabs_per_tap;
+          tma_load_4d(a_dst + (size_t)i * args.slab_bytes, &tmX, &full_bar[s], ck * SL,
+                      w0 + args.taps.dw[t], h0 + args.taps.dh[t], n0 + args.taps.dn[t]);
+        }
+        for (int i = 0; i < nb; ++i) {
+          tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
+                      nt * args.BN + i * SL, w0, h0, n0);
+        }
+        if (++s == args.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, args.BN, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t first = 1;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * args.stage_bytes);
+        const uint32_t b_addr = a_addr + b_off;
+        for (int k = 0; k < args.kmmas; ++k) {
+          const uint32_t koff = (uint32_t)k * 16u * Cfg::ROW_BYTES;
+          const uint64_t ad = make_smem_desc(a_addr + koff, Cfg::LBO, Cfg::SBO, Cfg::LAYOUT);
+          const uint64_t bd = make_smem_desc(b_addr + koff, Cfg::LBO, Cfg::SBO, Cfg::LAYOUT);
+          umma_bf16_ss(tmem_base, ad, bd, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == args.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(&tfull_bar);
+    }
+  } else if (pt1 > pt0) {
+    // epilogue: lane m of the accumulator is (slab, channel) = (m / SL, m % SL)
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const int q = q0 + m / SL;
+    const bool valid = q < args.nslabs_total;
+    int col = 0;
+    if (valid) {
+      const int t = q / args.slabs_per_tap;
+      const int ck = q % args.slabs_per_tap;
+      col = args.taps.wcol[t] + ck * SL + (m % SL);
+    }
+    float* drow = args.dw + (size_t)nt * args.BN * args.ktot + col;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    for (int c = 0; c < args.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(t_addr + c, v);
+      tmem_ld_wait();
+      if (valid) {
+        if (args.splits == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            drow[(size_t)(c + j) * args.ktot] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            atomicAdd(drow + (size_t)(c + j) * args.ktot, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,618 @@
+// HBM-bound kernels around the convolutions: batch-norm statistics, fused normalise + skip-add +
+// ReLU + dropout (forward and backward), subsample / upsample, parity split, pooling, layout casts.
+// All activations are NHWC bf16 handled as 16-byte vectors of 8 channels; per-channel quantities are
+// fp32; reductions are warp-shuffle / shared-memory trees with deterministic per-block partials.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int EW_THREADS = 256;
+constexpr int BN_MAX_BLOCKS = 1024;
+
+// -------------------------------------------------------------------------------------------------
+// Block-level per-channel reduction helper. Each thread owns one 8-channel group `cg` (fixed for
+// the whole kernel) and a row lane `rl`; acc[] holds NACC*8 per-channel partial sums of that thread.
+// The block reduces over row lanes and writes partial[blockIdx.x][a][C] for a < NACC.
+// -------------------------------------------------------------------------------------------------
+template <int NACC>
+__device__ __forceinline__ void block_channel_reduce(const float* acc, float* smem, int cgl, int rl,
+                                                     int CGb, int RP, bool active, float* partial,
+                                                     int C, int c_base) {
+  // smem layout: [RP][CGb*8*NACC]
+  const int width = CGb * 8 * NACC;
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[rl * width + (a * CGb + cgl) * 8 + j] = acc[a * 8 + j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < RP; ++r) s += smem[r * width + i];
+    const int a = i / (CGb * 8);
+    const int c = c_base + (i % (CGb * 8));
+    partial[((size_t)blockIdx.x * NACC + a) * C + c] = s;
+  }
+}
+
+// geometry shared by the reduction kernels: blockIdx.y selects a chunk of <=256 channel groups
+struct ReduceGeom {
+  int CG;    // C / 8
+  int CGb;   // channel groups handled by this block
+  int cg0;   // first channel group of this block
+  int RP;    // rows per pass
+  int cgl, rl;
+  bool active;
+  __device__ __forceinline__ ReduceGeom(int C) {
+    CG = C / 8;
+    cg0 = blockIdx.y * EW_THREADS;
+    CGb = min(EW_THREADS, CG - cg0);
+    RP = EW_THREADS / CGb;
+    cgl = threadIdx.x % CGb;
+    rl = threadIdx.x / CGb;
+    active = rl < RP;
+  }
+};
+
+// partial[b][0][c] = sum x, partial[b][1][c] = sum x^2 over the rows of block b
+__global__ void __launch_bounds__(EW_THREADS)
+bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* __restrict__ partial) {
+  extern __shared__ float red_smem[];
+  ReduceGeom g(C);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  if (g.active) {
+    const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    const bf16* base = x + (size_t)(g.cg0 + g.cgl) * 8;
+    for (int64_t r = r0 + g.rl; r < r1; r += g.RP) {
+      Vec8 v;
+      v.raw = ldg_stream(base + (size_t)r * C);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += f[j];
+        acc[8 + j] = fmaf(f[j], f[j], acc[8 + j]);
+      }
+    }
+  }
+  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, C, g.cg0 * 8);
+}
+
+// mean / invstd from the partials (+ running-stat update, torch.nn.BatchNorm2d semantics)
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t rows,
+                                         int C, float eps, float momentum, float* __restrict__ mean,
+                                         float* __restrict__ invstd, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var,
+                                         int64_t* __restrict__ num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((size_t)b * 2 + 0) * C + c];
+    ss += (double)partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const double m = s / (double)rows;
+  double var = ss / (double)rows - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward: y = dropout(act(bn(x) [+ skip]))
+// -------------------------------------------------------------------------------------------------
+struct BnActFwdArgs {
+  const bf16* x;
+  bf16* y;
+  const bf16* skip;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  int N, H, W, C;
+  int skip_mode, skip_C;
+  int stat_is_var, relu, affine;
+  float eps;
+  float inv_keep;
+  uint32_t drop_thr;  // drop when u16 < drop_thr
+  uint64_t seed;
+};
+
+__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdArgs a) {
+  extern __shared__ float ab_smem[];  // [2][C]: scale, shift
+  const int C = a.C;
+  if (a.affine) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float is = a.stat_is_var ? rsqrtf(a.invstd[c] + a.eps) : a.invstd[c];
+      const float sc = a.gamma[c] * is;
+      ab_smem[c] = sc;
+      ab_smem[C + c] = a.beta[c] - a.mean[c] * sc;
+    }
+    __syncthreads();
+  }
+  const int CG = C / 8;
+  const size_t nvec = (size_t)a.N * a.H * a.W * CG;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    Vec8 xv;
+    xv.raw = ldg_stream(a.x + v * 8);
+    float f[8];
+    xv.to_float(f);
+    if (a.affine) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        f[j] = round_bf16(fmaf(f[j], ab_smem[cg * 8 + j], ab_smem[C + cg * 8 + j]));
+    }
+    if (a.skip_mode == 1) {
+      Vec8 sv;
+      sv.raw = ldg_stream(a.skip + v * 8);
+      float s[8];
+      sv.to_float(s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + s[j]);
+    } else if (a.skip_mode == 2) {
+      if (cg * 8 < a.skip_C) {
+        const size_t pix = v / CG;
+        const int w = (int)(pix % a.W);
+        const int h = (int)((pix / a.W) % a.H);
+        const int n = (int)(pix / ((size_t)a.W * a.H));
+        const size_t spix = ((size_t)n * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w;
+        Vec8 sv;
+        sv.raw = ldg_stream(a.skip + spix * a.skip_C + (size_t)cg * 8);
+        float s[8];
+        sv.to_float(s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + s[j]);
+      }
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (a.drop_thr) {
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const uint32_t d = rng_draw(a.seed, v * 4 + j2);
+        f[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2] * a.inv_keep);
+        f[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2 + 1] * a.inv_keep);
+      }
+    }
+    Vec8 o;
+    o.from_float(f);
+    stg_stream(a.y + v * 8, o.raw);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------------
+struct BnActBwdArgs {
+  const bf16* dy;
+  const bf16* y;
+  const bf16* x;
+  bf16* dx;
+  bf16* dskip;
+  const bf16* addend;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  float* dgamma;
+  float* dbeta;
+  int64_t rows;
+  int C;
+  int relu, affine;
+  float inv_keep;
+  uint32_t drop_thr;
+  uint64_t seed;
+};
+
+// g = dy masked by relu (y != 0) and dropout (regenerated from the counter RNG), scaled by 1/(1-p)
+__device__ __forceinline__ void masked_grad(const BnActBwdArgs& a, size_t v, float* g) {
+  Vec8 dv;
+  dv.raw = ldg_stream(a.dy + v * 8);
+  dv.to_float(g);
+  if (a.drop_thr) {
+#pragma unroll
+    for (int j2 = 0; j2 < 4; ++j2) {
+      const uint32_t d = rng_draw(a.seed, v * 4 + j2);
+      g[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2] * a.inv_keep);
+      g[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2 + 1] * a.inv_keep);
+    }
+  }
+  if (a.relu) {
+    Vec8 yv;
+    yv.raw = ldg_stream(a.y + v * 8);
+    float yf[8];
+    yv.to_float(yf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = (yf[j] != 0.f) ? g[j] : 0.f;
+  }
+}
+
+// partial[b][0][c] = sum g, partial[b][1][c] = sum g * xhat
+__global__ void __launch_bounds__(EW_THREADS)
+bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
+  extern __shared__ float red_smem[];
+  ReduceGeom g(a.C);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  if (g.active) {
+    const int cgi = g.cg0 + g.cgl;
+    float mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = a.mean[cgi * 8 + j];
+      is[j] = a.invstd[cgi * 8 + j];
+    }
+    const int64_t rows_per_block = (a.rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(a.rows, r0 + rows_per_block);
+    for (int64_t r = r0 + g.rl; r < r1; r += g.RP) {
+      const size_t v = (size_t)r * g.CG + cgi;
+      float gr[8];
+      masked_grad(a, v, gr);
+      Vec8 xv;
+      xv.raw = ldg_stream(a.x + v * 8);
+      float xf[8];
+      xv.to_float(xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += gr[j];
+        acc[8 + j] = fmaf(gr[j], (xf[j] - mu[j]) * is[j], acc[8 + j]);
+      }
+    }
+  }
+  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, a.C,
+                          g.cg0 * 8);
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((size_t)b * 2 + 0) * C + c];
+    sx += (double)partial[((size_t)b * 2 + 1) * C + c];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)sx;
+}
+
+// dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g
+__global__ void __launch_bounds__(EW_THREADS) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
+  extern __shared__ float ch_smem[];  // [4][C]: mean, invstd, gamma*invstd, then dgamma/dbeta scaled
+  const int C = a.C;
+  if (a.affine) {
+    const float inv_rows = 1.f / (float)a.rows;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      ch_smem[c] = a.mean[c];
+      ch_smem[C + c] = a.invstd[c];
+      ch_smem[2 * C + c] = a.gamma[c] * a.invstd[c];
+      ch_smem[3 * C + c] = a.dbeta[c] * inv_rows;
+      ch_smem[4 * C + c] = a.dgamma[c] * inv_rows;
+    }
+    __syncthreads();
+  }
+  const int CG = C / 8;
+  const size_t nvec = (size_t)a.rows * CG;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    float g[8];
+    masked_grad(a, v, g);
+    if (a.dskip) {
+      Vec8 o;
+      o.from_float(g);
+      stg_stream(a.dskip + v * 8, o.raw);
+    }
+    float d[8];
+    if (a.affine) {
+      Vec8 xv;
+      xv.raw = ldg_stream(a.x + v * 8);
+      float xf[8];
+      xv.to_float(xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        const float xhat = (xf[j] - ch_smem[c]) * ch_smem[C + c];
+        d[j] = round_bf16(ch_smem[2 * C + c] *
+                          (g[j] - ch_smem[3 * C + c] - xhat * ch_smem[4 * C + c]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = g[j];
+    }
+    if (a.addend) {
+      Vec8 av;
+      av.raw = ldg_stream(a.addend + v * 8);
+      float af[8];
+      av.to_float(af);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = round_bf16(d[j] + af[j]);
+    }
+    Vec8 o;
+    o.from_float(d);
+    stg_stream(a.dx + v * 8, o.raw);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// subsample / upsample-add / parity split and merge
+// -------------------------------------------------------------------------------------------------
+// y[n,h,w,:] = x[n,2h,2w,:]   (y is [N,H,W,C], x is [N,2H,2W,C])
+__global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H,
+                                  int W, int C) {
+  const int CG = C / 8;
+  const size_t nvec = (size_t)N * H * W * CG;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    const size_t spix = ((size_t)n * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+    const uint4 t = ldg_stream(x + spix * C + (size_t)cg * 8);
+    stg_stream(y + v * 8, t);
+  }
+}
+
+// dx[n,2h,2w,c] = bf16(dx + g[n,h,w,c]) for c < Cg
+__global__ void upsample_add_kernel(bf16* __restrict__ dx, const bf16* __restrict__ g, int N, int H,
+                                    int W, int C, int Cg) {
+  const int CGg = Cg / 8;
+  const size_t nvec = (size_t)N * H * W * CGg;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CGg);
+    const size_t pix = v / CGg;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    const size_t dpix = ((size_t)n * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+    bf16* dp = dx + dpix * C + (size_t)cg * 8;
+    Vec8 a, b;
+    a.raw = *reinterpret_cast<const uint4*>(dp);
+    b.raw = ldg_stream(g + v * 8);
+    float fa[8], fb[8];
+    a.to_float(fa);
+    b.to_float(fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] = round_bf16(fa[j] + fb[j]);
+    a.from_float(fa);
+    *reinterpret_cast<uint4*>(dp) = a.raw;
+  }
+}
+
+// parity split: xs[(h%2)*2 + (w%2)][n][h/2][w/2][:] = x[n][h][w][:]; merge is the inverse
+template <bool MERGE>
+__global__ void parity_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int H,
+                              int W, int C) {
+  const int CG = C / 8;
+  const size_t nvec = (size_t)N * H * W * CG;
+  const int H2 = H / 2, W2 = W / 2;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    const int ph = (h & 1) * 2 + (w & 1);
+    const size_t ppix = (((size_t)ph * N + n) * H2 + (h >> 1)) * W2 + (w >> 1);
+    const size_t po = ppix * C + (size_t)cg * 8;
+    if (MERGE) stg_stream(dst + v * 8, ldg_stream(src + po));
+    else stg_stream(dst + po, ldg_stream(src + v * 8));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// layout: fp32 NCHW images -> bf16 NHWC; fp32 KRSC filters -> bf16 KRSC + bf16 CRSK
+// -------------------------------------------------------------------------------------------------
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y,
+                                             int N, int C, int H, int W) {
+  const size_t npix = (size_t)N * H * W;
+  const size_t hw = (size_t)H * W;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = p / hw, r = p % hw;
+    for (int c = 0; c < C; ++c)
+      y[p * C + c] = __float2bfloat16_rn(x[(n * C + c) * hw + r]);
+  }
+}
+
+__global__ void weight_cast_kernel(const float* __restrict__ w, bf16* __restrict__ o, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    o[i] = __float2bfloat16_rn(w[i]);
+}
+
+// w[K][RS][C] -> wt[C][RS][K]; 32x32 tiles over (K, C) for each filter tap (blockIdx.z)
+__global__ void weight_transpose_kernel(const float* __restrict__ w, bf16* __restrict__ wt, int K,
+                                        int RS, int C) {
+  __shared__ float tile[32][33];
+  const int rs = blockIdx.z;
+  const int k0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && c < C) ? w[((size_t)k * RS + rs) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, k = k0 + threadIdx.x;
+    if (k < K && c < C) wt[((size_t)c * RS + rs) * K + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// pooling
+// -------------------------------------------------------------------------------------------------
+struct PoolDims {
+  int N, H, W, C, k, stride, pad, P, Q;
+};
+
+// average pooling, count_include_pad = True (torch.nn.AvgPool2d default)
+__global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, PoolDims d) {
+  const int CG = d.C / 8;
+  const size_t nvec = (size_t)d.N * d.P * d.Q * CG;
+  const float inv = 1.f / (float)(d.k * d.k);
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int q = (int)(pix % d.Q);
+    const int p = (int)((pix / d.Q) % d.P);
+    const int n = (int)(pix / ((size_t)d.Q * d.P));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < d.k; ++r) {
+      const int h = p * d.stride + r - d.pad;
+      if (h < 0 || h >= d.H) continue;
+      for (int s = 0; s < d.k; ++s) {
+        const int w = q * d.stride + s - d.pad;
+        if (w < 0 || w >= d.W) continue;
+        Vec8 xv;
+        xv.raw = ldg_stream(x + (((size_t)n * d.H + h) * d.W + w) * d.C + (size_t)cg * 8);
+        float f[8];
+        xv.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    Vec8 o;
+    o.from_float(acc);
+    stg_stream(y + v * 8, o.raw);
+  }
+}
+
+__global__ void avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, PoolDims d) {
+  const int CG = d.C / 8;
+  const size_t nvec = (size_t)d.N * d.H * d.W * CG;
+  const float inv = 1.f / (float)(d.k * d.k);
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int w = (int)(pix % d.W);
+    const int h = (int)((pix / d.W) % d.H);
+    const int n = (int)(pix / ((size_t)d.W * d.H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < d.k; ++r) {
+      const int hp = h + d.pad - r;
+      if (hp < 0 || (hp % d.stride) != 0) continue;
+      const int p = hp / d.stride;
+      if (p >= d.P) continue;
+      for (int s = 0; s < d.k; ++s) {
+        const int wp = w + d.pad - s;
+        if (wp < 0 || (wp % d.stride) != 0) continue;
+        const int q = wp / d.stride;
+        if (q >= d.Q) continue;
+        Vec8 g;
+        g.raw = ldg_stream(dy + (((size_t)n * d.P + p) * d.Q + q) * d.C + (size_t)cg * 8);
+        float f[8];
+        g.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += round_bf16(f[j] * inv);
+      }
+    }
+    Vec8 o;
+    o.from_float(acc);
+    stg_stream(dx + v * 8, o.raw);
+  }
+}
+
+// max pooling (padding behaves as -inf)
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, PoolDims d) {
+  const int CG = d.C / 8;
+  const size_t nvec = (size_t)d.N * d.P * d.Q * CG;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
+    const int q = (int)(pix % d.Q);
+    const int p = (int)((pix / d.Q) % d.P);
+    const int n = (int)(pix / ((size_t)d.Q * d.P));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int r = 0; r < d.k; ++r) {
+      const int h = p * d.stride + r - d.pad;
+      if (h < 0 || h >= d.H) continue;
+      for (int s = 0; s < d.k; ++s) {
+        const int w = q * d.stride + s - d.pad;
+        if (w < 0 || w >= d.W) continue;
+        Vec8 xv;
+        xv.raw = ldg_stream(x + (((size_t)n * d.H + h) * d.W + w) * d.C + (size_t)cg * 8);
+        float f[8];
+        xv.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    Vec8 o;
+    o.from_float(m);
+    stg_stream(y + v * 8, o.raw);
+  }
+}
+
+// gather form of max-pool backward: an input element receives dy of every window whose first
+// maximum (row-major scan order, as torch's max_pool2d_with_indices) is that element.
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                   bf16* __restrict__ dx, PoolDims d) {
+  const size_t total = (size_t)d.N * d.H * d.W * d.C;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % d.C);
+    const size_t pix = idx / d.C;
+    const int w = (int)(pix % d.W);
+    const int h = (int)((pix / d.W) % d.H);
+    const int n = (int)(pix / ((size_t)d.W * d.H));
+    const float xv = __bfloat162float(x[idx]);
+    float acc = 0.f;
+    for (int r = 0; r < d.k; ++r) {
+      const int hp = h + d.pad - r;
+      if (hp < 0 || (hp % d.stride) != 0) continue;
+      const int p = hp / d.stride;
+      if (p >= d.P) continue;
+      for (int s = 0; s < d.k; ++s) {
+        const int wp = w + d.pad - s;
+        if (wp < 0 || (wp % d.stride) != 0) continue;
+        const int q = wp / d.stride;
+        if (q >= d.Q) continue;
+        // is (h, w) the first maximum of window (p, q)?
+        bool is_arg = true;
+        for (int r2 = 0; r2 < d.k && is_arg; ++r2) {
+          const int h2 = p * d.stride + r2 - d.pad;
+          if (h2 < 0 || h2 >= d.H) continue;
+          for (int s2 = 0; s2 < d.k; ++s2) {
+            const int w2 = q * d.stride + s2 - d.pad;
+            if (w2 < 0 || w2 >= d.W) continue;
+            const float o = __bfloat162float(x[(((size_t)n * d.H + h2) * d.W + w2) * d.C + c]);
+            const bool before = (h2 < h) || (h2 == h && w2 < w);
+            if (o > xv || (before && o == xv)) { is_arg = false; break; }
+          }
+        }
+        if (is_arg) acc += __bfloat162float(dy[(((size_t)n * d.P + p) * d.Q + q) * d.C + c]);
+      }
+    }
+    dx[idx] = __float2bfloat16_rn(acc);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,303 @@
+"""
+Raw kernel wrappers: torch tensors in, torch tensors out, no autograd. Every function here is one or
+two launches of a kernel in libb200resnet.so on the *current* torch CUDA stream.
+
+Conventions (see include/b200resnet.h):
+  * activations: contiguous bf16 tensors of shape [N, H, W, C] (NHWC);
+  * conv filters: bf16 [K, R, S, C] (KRSC) and bf16 [C, R, S, K] (CRSK) working copies;
+  * everything per-channel / per-parameter is fp32.
+"""
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from pytorch_ddp_resnet_b200 import _lib
+
+_ALGO_NAMES = {"auto": _lib.ALGO_AUTO, "direct": _lib.ALGO_DIRECT, "tc": _lib.ALGO_TC}
+_workspaces = {}
+
+
+def conv_algo() -> int:
+    """Conv algorithm from B200_CONV_ALGO (auto | direct | tc); 'auto' uses tcgen05 when it can."""
+    return _ALGO_NAMES[os.environ.get("B200_CONV_ALGO", "auto")]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _check_act(t: torch.Tensor, name: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+        raise _lib.B200Error(
+            f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device} "
+            f"contiguous={t.is_contiguous()}")
+    _lib.require_device(t.device.index or 0)
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------------------------------
+# filters / layout
+# --------------------------------------------------------------------------------------------------
+def weight_prep(w_krsc_f32: torch.Tensor, want_crsk: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 [K,R,S,C] master -> (bf16 [K,R,S,C], bf16 [C,R,S,K])."""
+    assert w_krsc_f32.dtype == torch.float32 and w_krsc_f32.is_contiguous() and w_krsc_f32.is_cuda
+    _lib.require_device(w_krsc_f32.device.index or 0)
+    K, R, S, C = w_krsc_f32.shape
+    wk = torch.empty((K, R, S, C), dtype=torch.bfloat16, device=w_krsc_f32.device)
+    wt = torch.empty((C, R, S, K), dtype=torch.bfloat16, device=w_krsc_f32.device) if want_crsk else None
+    _lib.call("b200_weight_prep", w_krsc_f32.data_ptr(), wk.data_ptr(), _p(wt), K, R * S, C, _stream())
+    return wk, wt
+
+
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda and x.dim() == 4
+    _lib.require_device(x.device.index or 0)
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    _lib.call("b200_nchw_f32_to_nhwc_bf16", x.data_ptr(), y.data_ptr(), N, C, H, W, _stream())
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------------
+def _out_hw(H, W, R, S, stride, pad):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=None):
+    _check_act(x, "conv_fprop.x")
+    N, H, W, C = x.shape
+    K, R, S, Cw = w_krsc.shape
+    assert Cw == C and w_krsc.dtype == torch.bfloat16 and w_krsc.is_contiguous()
+    P, Q = _out_hw(H, W, R, S, stride, pad)
+    y = torch.empty((N, P, Q, K), dtype=torch.bfloat16, device=x.device)
+    if residual is not None:
+        _check_act(residual, "conv_fprop.residual")
+        assert residual.shape == y.shape
+    algo = conv_algo() if algo is None else algo
+    nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_FPROP, N, H, W, C, K, R, S, stride, pad, algo)
+    ws = _workspace(x.device, nws) if nws else None
+    _lib.call("b200_conv2d_fprop", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
+              y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
+    return y
+
+
+def conv_dgrad(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, addend=None, algo=None):
+    _check_act(dy, "conv_dgrad.dy")
+    N, P, Q, K = dy.shape
+    C, R, S, Kw = w_crsk.shape
+    assert Kw == K and w_crsk.dtype == torch.bfloat16 and w_crsk.is_contiguous()
+    H, W = in_hw
+    assert _out_hw(H, W, R, S, stride, pad) == (P, Q)
+    dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
+    if addend is not None:
+        _check_act(addend, "conv_dgrad.addend")
+        assert addend.shape == dx.shape
+    algo = conv_algo() if algo is None else algo
+    nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_DGRAD, N, H, W, C, K, R, S, stride, pad, algo)
+    ws = _workspace(dy.device, nws) if nws else None
+    _lib.call("b200_conv2d_dgrad", dy.data_ptr(), w_crsk.data_ptr(), _p(addend), dx.data_ptr(),
+              N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
+    return dx
+
+
+def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = False, algo=None):
+    """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None)."""
+    _check_act(dy, "conv_wgrad.dy")
+    _check_act(x, "conv_wgrad.x")
+    N, H, W, C = x.shape
+    Nd, P, Q, K = dy.shape
+    assert Nd == N and _out_hw(H, W, R, S, stride, pad) == (P, Q)
+    dw = torch.empty((K, R, S, C), dtype=torch.float32, device=x.device)
+    db = torch.empty((K,), dtype=torch.float32, device=x.device) if want_dbias else None
+    algo = conv_algo() if algo is None else algo
+    nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_WGRAD, N, H, W, C, K, R, S, stride, pad, algo)
+    ws = _workspace(x.device, nws) if nws else None
+    _lib.call("b200_conv2d_wgrad", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _p(db),
+              N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
+    return dw, db
+
+
+def conv_tc_supported(pass_: int, N, H, W, C, K, R, S, stride, pad) -> bool:
+    return bool(_lib.load().b200_conv2d_tc_supported(pass_, N, H, W, C, K, R, S, stride, pad))
+
+
+# --------------------------------------------------------------------------------------------------
+# batch norm / activation / dropout / skip
+# --------------------------------------------------------------------------------------------------
+def bn_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_var=None,
+             num_batches_tracked=None):
+    """Batch statistics of an [..., C] bf16 tensor -> (mean, invstd); updates running stats in place."""
+    _check_act(x, "bn_stats.x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    mean = torch.empty((C,), dtype=torch.float32, device=x.device)
+    invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
+    nws = _lib.load().b200_bn_workspace_bytes(rows, C)
+    ws = _workspace(x.device, nws)
+    _lib.call("b200_bn_stats", x.data_ptr(), rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
+              _p(running_mean), _p(running_var), _p(num_batches_tracked), ws.data_ptr(), nws, _stream())
+    return mean, invstd
+
+
+def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var: bool = False,
+               eps: float = 1e-5, skip=None, skip_mode: int = _lib.SKIP_NONE, relu: bool = True,
+               dropout_p: float = 0.0, seed: int = 0):
+    _check_act(x, "bn_act_fwd.x")
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    skip_C = 0
+    if skip is not None:
+        _check_act(skip, "bn_act_fwd.skip")
+        skip_C = skip.shape[-1]
+        if skip_mode == _lib.SKIP_SAME:
+            assert skip.shape == x.shape
+        else:
+            assert skip.shape[0] == N and skip.shape[1] == 2 * H and skip.shape[2] == 2 * W
+    _lib.call("b200_bn_act_fwd", x.data_ptr(), y.data_ptr(), N, H, W, C, _p(mean), _p(invstd),
+              int(stat_is_var), eps, _p(gamma), _p(beta), _p(skip), skip_mode if skip is not None else 0,
+              skip_C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+    return y
+
+
+def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = True,
+               dropout_p: float = 0.0, seed: int = 0, addend=None, want_dskip: bool = False):
+    """Returns (dx, dgamma, dbeta, dskip)."""
+    _check_act(dy, "bn_act_bwd.dy")
+    C = dy.shape[-1]
+    rows = dy.numel() // C
+    dx = torch.empty_like(dy)
+    dskip = torch.empty_like(dy) if want_dskip else None
+    affine = gamma is not None
+    dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
+    dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
+    nws = _lib.load().b200_bn_workspace_bytes(rows, C) if affine else 0
+    ws = _workspace(dy.device, nws) if affine else None
+    if addend is not None:
+        _check_act(addend, "bn_act_bwd.addend")
+        assert addend.shape == dy.shape
+    _lib.call("b200_bn_act_bwd", dy.data_ptr(), _p(y), _p(x), dx.data_ptr(), _p(dskip), _p(addend), rows,
+              C, _p(mean), _p(invstd), _p(gamma), _p(dgamma), _p(dbeta), int(relu), float(dropout_p),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, _p(ws), nws, _stream())
+    return dx, dgamma, dbeta, dskip
+
+
+def subsample2(x):
+    _check_act(x, "subsample2.x")
+    N, H2, W2, C = x.shape
+    assert H2 % 2 == 0 and W2 % 2 == 0
+    y = torch.empty((N, H2 // 2, W2 // 2, C), dtype=torch.bfloat16, device=x.device)
+    _lib.call("b200_subsample2", x.data_ptr(), y.data_ptr(), N, H2 // 2, W2 // 2, C, _stream())
+    return y
+
+
+def upsample_add_(dx, g):
+    """dx[n, 2h, 2w, :Cg] += g[n, h, w, :] in place."""
+    _check_act(dx, "upsample_add.dx")
+    _check_act(g, "upsample_add.g")
+    N, H, W, Cg = g.shape
+    assert dx.shape[0] == N and dx.shape[1] == 2 * H and dx.shape[2] == 2 * W and dx.shape[3] >= Cg
+    _lib.call("b200_upsample_add", dx.data_ptr(), g.data_ptr(), N, H, W, dx.shape[3], Cg, _stream())
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------
+# pooling
+# --------------------------------------------------------------------------------------------------
+def _pool(name, x, k, stride, pad):
+    _check_act(x, name)
+    N, H, W, C = x.shape
+    P, Q = _out_hw(H, W, k, k, stride, pad)
+    y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=x.device)
+    _lib.call(name, x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, _stream())
+    return y
+
+
+def avgpool_fwd(x, k, stride, pad):
+    return _pool("b200_avgpool_fwd", x, k, stride, pad)
+
+
+def maxpool_fwd(x, k, stride, pad):
+    return _pool("b200_maxpool_fwd", x, k, stride, pad)
+
+
+def avgpool_bwd(dy, in_shape, k, stride, pad):
+    _check_act(dy, "avgpool_bwd.dy")
+    N, H, W, C = in_shape
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    _lib.call("b200_avgpool_bwd", dy.data_ptr(), dx.data_ptr(), N, H, W, C, k, stride, pad, _stream())
+    return dx
+
+
+def maxpool_bwd(dy, x, y, k, stride, pad):
+    _check_act(dy, "maxpool_bwd.dy")
+    N, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("b200_maxpool_bwd", dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), N, H, W, C, k,
+              stride, pad, _stream())
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------
+# head
+# --------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, b):
+    _check_act(x, "linear_fwd.x")
+    B, I = x.shape
+    O = w.shape[0]
+    y = torch.empty((B, O), dtype=torch.bfloat16, device=x.device)
+    _lib.call("b200_linear_fwd", x.data_ptr(), w.data_ptr(), _p(b), y.data_ptr(), B, I, O, _stream())
+    return y
+
+
+def linear_bwd(dy, x, w, want_dx=True):
+    _check_act(dy, "linear_bwd.dy")
+    B, O = dy.shape
+    I = x.shape[1]
+    dx = torch.empty((B, I), dtype=torch.bfloat16, device=dy.device) if want_dx else None
+    dw = torch.empty((O, I), dtype=torch.float32, device=dy.device)
+    db = torch.empty((O,), dtype=torch.float32, device=dy.device)
+    _lib.call("b200_linear_bwd", dy.data_ptr(), x.data_ptr(), w.data_ptr(), _p(dx), dw.data_ptr(),
+              db.data_ptr(), B, I, O, _stream())
+    return dx, dw, db
+
+
+def ce_topk(logits, labels, want_metrics=True, want_dlogits=False, grad_scale=None):
+    """(out fp32[3] = loss, top1_err, top5_err | None, dlogits bf16 | None)."""
+    _check_act(logits, "ce_topk.logits")
+    assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous()
+    B, O = logits.shape
+    out = torch.empty((3,), dtype=torch.float32, device=logits.device) if want_metrics else None
+    dl = torch.empty_like(logits) if want_dlogits else None
+    _lib.call("b200_ce_topk", logits.data_ptr(), labels.data_ptr(), _p(out), _p(dl), _p(grad_scale), B, O,
+              _stream())
+    return out, dl
+
+
+# --------------------------------------------------------------------------------------------------
+# optimizer
+# --------------------------------------------------------------------------------------------------
+def sgd_step(ptr_table: torch.Tensor, n: int, max_size: int, lr, momentum, dampening, weight_decay,
+             nesterov, first_step, inv_scale=None, found_inf=None):
+    """ptr_table: int64 CUDA tensor [4, n] = rows of param ptrs, grad ptrs, buf ptrs, sizes."""
+    assert ptr_table.dtype == torch.int64 and ptr_table.is_cuda and ptr_table.shape == (4, n)
+    _lib.require_device(ptr_table.device.index or 0)
+    base = ptr_table.data_ptr()
+    row = n * 8
+    _lib.call("b200_sgd_step", base, base + row, base + 2 * row, base + 3 * row, n, max_size, float(lr),
+              float(momentum), float(dampening), float(weight_decay), int(bool(nesterov)),
+              int(bool(first_step)), _p(inv_scale), _p(found_inf), _stream())

@@ -1,0 +1,307 @@
+"""
+GPU parity of every kernel in libb200resnet.so (called through the C ABI via ctypes) against a plain
+torch fp32 reference of the same op on identical bf16-rounded inputs.
+Tolerances: bf16 outputs carry one bf16 rounding (2^-9 relative) on top of fp32 accumulation order
+=> relative L2 <= 4e-3; fp32 outputs (weight gradients, statistics) <= 1e-3 relative L2 / 1e-4.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exact_fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from pytorch_ddp_resnet_b200 import ops, _lib
+    return ops, _lib
+
+
+def nhwc(t):  # [N,H,W,C] -> NCHW view for torch
+    return t.permute(0, 3, 1, 2)
+
+
+# N, H, W, C, K, R, stride, pad
+CONV_SHAPES = [
+    (2, 8, 8, 16, 16, 3, 1, 1),
+    (4, 32, 32, 16, 16, 3, 1, 1),
+    (4, 16, 16, 32, 64, 3, 1, 1),
+    (4, 16, 16, 64, 32, 1, 1, 0),
+    (8, 8, 8, 64, 64, 3, 1, 1),
+    (4, 32, 32, 160, 160, 3, 1, 1),
+    (4, 16, 16, 320, 320, 3, 1, 1),
+    (4, 8, 8, 640, 640, 3, 1, 1),
+    (4, 32, 32, 160, 320, 3, 2, 1),
+    (4, 16, 16, 320, 640, 3, 2, 1),
+    (4, 16, 16, 160, 320, 1, 1, 0),
+    (2, 32, 32, 16, 32, 3, 2, 1),
+    (6, 8, 8, 32, 48, 3, 1, 1),
+    (3, 16, 16, 48, 32, 3, 1, 1),
+]
+
+
+def _conv_inputs(N, H, W, C, K, R, stride, pad, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(K, R, R, C, device="cuda", generator=g) / (C * R * R) ** 0.5).bfloat16()
+    P = (H + 2 * pad - R) // stride + 1
+    dy = torch.randn(N, P, P, K, device="cuda", generator=g).bfloat16()
+    return x, w, dy
+
+
+@pytest.mark.parametrize("algo", ["tc", "direct"])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fprop(shape, algo):
+    ops, _lib = _ops()
+    N, H, W, C, K, R, stride, pad = shape
+    a = {"tc": _lib.ALGO_TC, "direct": _lib.ALGO_DIRECT}[algo]
+    x, w, _ = _conv_inputs(*shape)
+    res = torch.randn(N, (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1, K,
+                      device="cuda").bfloat16()
+    ref = F.conv2d(nhwc(x).float(), w.permute(0, 3, 1, 2).float(), stride=stride, padding=pad)
+    y = ops.conv_fprop(x, w, stride, pad, algo=a)
+    assert rel_l2(nhwc(y), ref) < 4e-3
+    y2 = ops.conv_fprop(x, w, stride, pad, residual=res, algo=a)
+    ref2 = ref.bfloat16().float() + nhwc(res).float()
+    assert rel_l2(nhwc(y2), ref2) < 4e-3
+
+
+@pytest.mark.parametrize("algo", ["tc", "direct"])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad(shape, algo):
+    ops, _lib = _ops()
+    N, H, W, C, K, R, stride, pad = shape
+    a = {"tc": _lib.ALGO_TC, "direct": _lib.ALGO_DIRECT}[algo]
+    x, w, dy = _conv_inputs(*shape)
+    w_crsk = w.permute(3, 1, 2, 0).contiguous()
+    ref = torch.nn.grad.conv2d_input((N, C, H, W), w.permute(0, 3, 1, 2).float(), nhwc(dy).float(),
+                                     stride=stride, padding=pad)
+    dx = ops.conv_dgrad(dy, w_crsk, (H, W), stride, pad, algo=a)
+    assert rel_l2(nhwc(dx), ref) < 4e-3
+    add = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    dx2 = ops.conv_dgrad(dy, w_crsk, (H, W), stride, pad, addend=add, algo=a)
+    assert rel_l2(nhwc(dx2), ref.bfloat16().float() + nhwc(add).float()) < 4e-3
+
+
+@pytest.mark.parametrize("algo", ["tc", "direct"])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_wgrad(shape, algo):
+    ops, _lib = _ops()
+    N, H, W, C, K, R, stride, pad = shape
+    a = {"tc": _lib.ALGO_TC, "direct": _lib.ALGO_DIRECT}[algo]
+    x, w, dy = _conv_inputs(*shape)
+    ref = torch.nn.grad.conv2d_weight(nhwc(x).float(), (K, C, R, R), nhwc(dy).float(), stride=stride,
+                                      padding=pad)
+    dw, db = ops.conv_wgrad(dy, x, R, R, stride, pad, want_dbias=True, algo=a)
+    assert rel_l2(dw.permute(0, 3, 1, 2), ref) < 1e-3
+    assert rel_l2(db, dy.float().sum((0, 1, 2))) < 1e-3
+
+
+def test_stem_direct_conv():
+    ops, _lib = _ops()
+    x = torch.randn(8, 3, 32, 32, device="cuda")
+    w = torch.randn(160, 3, 3, 3, device="cuda") * 0.27
+    b = torch.randn(160, device="cuda") * 0.1
+    xh = ops.nchw_f32_to_nhwc_bf16(x)
+    assert torch.equal(nhwc(xh), x.bfloat16())
+    wk = w.permute(0, 2, 3, 1).contiguous().bfloat16()
+    y = ops.conv_fprop(xh, wk, 1, 1, bias=b)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b.bfloat16().float(), padding=1)
+    assert rel_l2(nhwc(y), ref) < 4e-3
+    dy = torch.randn(8, 32, 32, 160, device="cuda").bfloat16()
+    dw, db = ops.conv_wgrad(dy, xh, 3, 3, 1, 1, want_dbias=True)
+    refw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (160, 3, 3, 3), nhwc(dy).float(), padding=1)
+    assert rel_l2(dw.permute(0, 3, 1, 2), refw) < 1e-3
+
+
+def test_weight_prep():
+    ops, _ = _ops()
+    w = torch.randn(48, 3, 3, 40, device="cuda")
+    wk, wt = ops.weight_prep(w)
+    assert torch.equal(wk, w.bfloat16())
+    assert torch.equal(wt, w.bfloat16().permute(3, 1, 2, 0).contiguous())
+
+
+@pytest.mark.parametrize("shape", [(4, 32, 32, 160), (8, 8, 8, 640), (3, 5, 7, 16), (2, 4, 4, 4096)])
+def test_bn_stats(shape):
+    ops, _ = _ops()
+    x = (torch.randn(*shape, device="cuda") * 1.7 + 0.4).bfloat16()
+    C = shape[-1]
+    rm = torch.zeros(C, device="cuda")
+    rv = torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    mean, invstd = ops.bn_stats(x, 1e-5, 0.1, rm, rv, nbt)
+    xf = x.float().reshape(-1, C)
+    m_ref = xf.mean(0)
+    v_ref = xf.var(0, unbiased=False)
+    assert torch.allclose(mean, m_ref, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(invstd, (v_ref + 1e-5).rsqrt(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(rm, 0.1 * m_ref, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(rv, 0.9 + 0.1 * xf.var(0, unbiased=True), atol=1e-4, rtol=1e-4)
+    assert nbt.item() == 1
+
+
+@pytest.mark.parametrize("C", [16, 160, 640])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_act_fwd_bwd_matches_autograd(C, relu):
+    ops, _lib = _ops()
+    N, H, W = 4, 8, 8
+    x = (torch.randn(N, H, W, C, device="cuda") * 1.3 + 0.2).bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.1
+    skip = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    dy = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    mean, invstd = ops.bn_stats(x, 1e-5)
+    for use_skip in (False, True):
+        y = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=relu,
+                           skip=skip if use_skip else None, skip_mode=_lib.SKIP_SAME)
+        xr = x.float().requires_grad_(True)
+        gr = gamma.clone().requires_grad_(True)
+        br = beta.clone().requires_grad_(True)
+        sr = skip.float().requires_grad_(True)
+        t = F.batch_norm(xr.reshape(-1, C), None, None, gr, br, True, 0.1, 1e-5).reshape(N, H, W, C)
+        if use_skip:
+            t = t + sr
+        ref = torch.relu(t) if relu else t
+        assert rel_l2(y, ref) < 4e-3
+        ref.backward(dy.float())
+        dx, dgamma, dbeta, dskip = ops.bn_act_bwd(dy, y, x, mean, invstd, gamma, relu=relu,
+                                                  want_dskip=use_skip)
+        # the kernel masks with ITS OWN y; near-zero pre-activations may flip: compare in bulk norms
+        assert rel_l2(dx, xr.grad) < 2e-2
+        assert rel_l2(dgamma, gr.grad) < 2e-2
+        assert rel_l2(dbeta, br.grad) < 2e-2
+        if use_skip:
+            assert rel_l2(dskip, sr.grad) < 2e-2
+
+
+def test_bn_act_eval_mode_and_subsample_pad_skip():
+    ops, _lib = _ops()
+    N, H, W, C, Cs = 2, 4, 4, 32, 16
+    x = torch.randn(N, H, W, C, device="cuda").bfloat16()
+    rm = torch.randn(C, device="cuda") * 0.1
+    rv = torch.rand(C, device="cuda") + 0.5
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.1
+    big = torch.randn(N, 2 * H, 2 * W, Cs, device="cuda").bfloat16()
+    y = ops.bn_act_fwd(x, rm, rv, gamma, beta, stat_is_var=True, skip=big,
+                       skip_mode=_lib.SKIP_SUBSAMPLE_PAD, relu=True)
+    ref = F.batch_norm(x.float().reshape(-1, C), rm, rv, gamma, beta, False, 0.1, 1e-5).reshape(N, H, W, C)
+    sk = F.pad(big[:, ::2, ::2, :].float(), (0, C - Cs))
+    ref = torch.relu(ref.bfloat16().float() + sk)
+    assert rel_l2(y, ref) < 4e-3
+
+
+def test_dropout_statistics_and_backward_mask():
+    ops, _ = _ops()
+    x = torch.ones(8, 32, 32, 160, device="cuda").bfloat16()
+    p = 0.3
+    y = ops.bn_act_fwd(x, relu=False, dropout_p=p, seed=1234)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 2e-3
+    kept_vals = y[y != 0].float()
+    assert torch.allclose(kept_vals, torch.full_like(kept_vals, 1 / (1 - p)), rtol=4e-3)
+    y2 = ops.bn_act_fwd(x, relu=False, dropout_p=p, seed=1234)
+    assert torch.equal(y, y2)
+    y3 = ops.bn_act_fwd(x, relu=False, dropout_p=p, seed=99)
+    assert not torch.equal(y, y3)
+    dx, _, _, _ = ops.bn_act_bwd(x, None, None, relu=False, dropout_p=p, seed=1234)
+    assert torch.equal(dx != 0, y != 0)
+    # per-channel keep rate is uniform
+    ch = (y != 0).float().mean((0, 1, 2))
+    assert (ch - (1 - p)).abs().max().item() < 2e-2
+
+
+def test_subsample_upsample():
+    ops, _ = _ops()
+    x = torch.randn(2, 8, 8, 32, device="cuda").bfloat16()
+    y = ops.subsample2(x)
+    assert torch.equal(y, x[:, ::2, ::2, :])
+    dx = torch.randn(2, 8, 8, 32, device="cuda").bfloat16()
+    g = torch.randn(2, 4, 4, 16, device="cuda").bfloat16()
+    ref = dx.clone().float()
+    ref[:, ::2, ::2, :16] += g.float()
+    ops.upsample_add_(dx, g)
+    assert torch.equal(dx, ref.bfloat16())
+
+
+@pytest.mark.parametrize("k,s,p,H", [(8, 1, 0, 8), (3, 2, 1, 16), (2, 2, 0, 8)])
+def test_pools(k, s, p, H):
+    ops, _ = _ops()
+    x = torch.randn(2, H, H, 32, device="cuda").bfloat16()
+    xa = nhwc(x).float().requires_grad_(True)
+    ref = F.avg_pool2d(xa, k, s, p)
+    y = ops.avgpool_fwd(x, k, s, p)
+    assert rel_l2(nhwc(y), ref) < 4e-3
+    dy = torch.randn_like(y)
+    ref.backward(nhwc(dy).float())
+    dx = ops.avgpool_bwd(dy, tuple(x.shape), k, s, p)
+    assert rel_l2(nhwc(dx), xa.grad) < 8e-3
+    xm = nhwc(x).float().requires_grad_(True)
+    refm = F.max_pool2d(xm, k, s, p)
+    ym = ops.maxpool_fwd(x, k, s, p)
+    assert torch.equal(nhwc(ym).float(), refm)
+    refm.backward(nhwc(dy).float())
+    dxm = ops.maxpool_bwd(dy, x, ym, k, s, p)
+    assert rel_l2(nhwc(dxm), xm.grad) < 4e-3
+
+
+def test_linear_and_ce():
+    ops, _ = _ops()
+    B, I, O = 128, 640, 10
+    x = torch.randn(B, I, device="cuda").bfloat16()
+    w = torch.randn(O, I, device="cuda") * 0.05
+    b = torch.randn(O, device="cuda") * 0.1
+    y = ops.linear_fwd(x, w, b)
+    ref = x.float() @ w.bfloat16().float().t() + b.bfloat16().float()
+    assert rel_l2(y, ref) < 4e-3
+    labels = torch.randint(0, O, (B,), device="cuda")
+    out, dl = ops.ce_topk(y, labels, want_dlogits=True)
+    yl = y.float().requires_grad_(True)
+    loss = F.cross_entropy(yl, labels)
+    loss.backward()
+    assert abs(out[0].item() - loss.item()) < 1e-4
+    top1 = 1 - (yl.argmax(-1) == labels).float().mean().item()
+    top5 = 1 - (yl.topk(5, -1).indices == labels[:, None]).any(-1).float().mean().item()
+    assert abs(out[1].item() - top1) < 1e-6 and abs(out[2].item() - top5) < 1e-6
+    assert rel_l2(dl, yl.grad) < 4e-3
+    dx, dw, db = ops.linear_bwd(dl, x, w)
+    assert rel_l2(dx, dl.float() @ w.bfloat16().float()) < 4e-3
+    assert rel_l2(dw, dl.float().t() @ x.float()) < 1e-4
+    assert rel_l2(db, dl.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_sgd_matches_torch(nesterov):
+    ops, _ = _ops()
+    torch.manual_seed(0)
+    shapes = [(160, 3, 3, 160), (7,), (640, 10), (1,), (33, 5)]
+    ps = [torch.randn(*s, device="cuda") for s in shapes]
+    ref_ps = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.SGD(ref_ps, lr=0.1, momentum=0.9, dampening=0.0, nesterov=nesterov,
+                          weight_decay=5e-4)
+    bufs = [torch.zeros_like(p) for p in ps]
+    for step in range(3):
+        gs = [torch.randn_like(p) for p in ps]
+        for rp, g in zip(ref_ps, gs):
+            rp.grad = g.clone()
+        opt.step()
+        table = torch.tensor([[p.data_ptr() for p in ps], [g.data_ptr() for g in gs],
+                              [b.data_ptr() for b in bufs], [p.numel() for p in ps]],
+                             dtype=torch.int64).cuda()
+        ops.sgd_step(table, len(ps), max(p.numel() for p in ps), 0.1, 0.9, 0.0, 5e-4, nesterov,
+                     step == 0)
+        for p, rp in zip(ps, ref_ps):
+            assert torch.allclose(p, rp.detach(), atol=1e-6, rtol=1e-5)

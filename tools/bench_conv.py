@@ -1,0 +1,72 @@
+"""Per-shape timing of the conv kernels (CUDA events, rotating buffers larger than L2) with the
+torch/cuDNN bf16 channels_last time of the same op beside it. Writes gpurun_out/bench_conv.json."""
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pytorch_ddp_resnet_b200 import ops, _lib  # noqa: E402
+
+SHAPES = [  # N, H, W, C, K, R, stride, pad  (WRN-28-10, batch 128)
+    (128, 32, 32, 160, 160, 3, 1, 1),
+    (128, 16, 16, 320, 320, 3, 1, 1),
+    (128, 8, 8, 640, 640, 3, 1, 1),
+    (128, 32, 32, 160, 320, 3, 2, 1),
+    (128, 16, 16, 320, 640, 3, 2, 1),
+    (128, 16, 16, 160, 320, 1, 1, 0),
+]
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    res = []
+    NB = 6  # rotating buffers
+    for (N, H, W, C, K, R, st, pad) in SHAPES:
+        P = (H + 2 * pad - R) // st + 1
+        xs = [torch.randn(N, H, W, C, device="cuda").bfloat16() for _ in range(NB)]
+        dys = [torch.randn(N, P, P, K, device="cuda").bfloat16() for _ in range(NB)]
+        w = (torch.randn(K, R, R, C, device="cuda") * 0.02).bfloat16()
+        wt = w.permute(3, 1, 2, 0).contiguous()
+        flops = 2.0 * N * P * P * K * C * R * R
+        row = {"shape": [N, H, W, C, K, R, st, pad], "gflop": flops / 1e9}
+        for name, fn in [
+            ("fprop", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC)),
+            ("dgrad", lambda i: ops.conv_dgrad(dys[i % NB], wt, (H, W), st, pad, algo=_lib.ALGO_TC)),
+            ("wgrad", lambda i: ops.conv_wgrad(dys[i % NB], xs[i % NB], R, R, st, pad, algo=_lib.ALGO_TC)),
+        ]:
+            ms = timeit(fn)
+            row[name + "_ms"] = ms
+            row[name + "_tflops"] = flops / ms / 1e9
+        # cuDNN bf16 channels_last for context
+        xc = [x.permute(0, 3, 1, 2) for x in xs]
+        wc = w.permute(0, 3, 1, 2)
+        dyc = [d.permute(0, 3, 1, 2) for d in dys]
+        row["cudnn_fprop_ms"] = timeit(lambda i: F.conv2d(xc[i % NB], wc, stride=st, padding=pad))
+        row["cudnn_dgrad_ms"] = timeit(lambda i: torch.nn.grad.conv2d_input(
+            (N, C, H, W), wc, dyc[i % NB], stride=st, padding=pad))
+        row["cudnn_wgrad_ms"] = timeit(lambda i: torch.nn.grad.conv2d_weight(
+            xc[i % NB], (K, C, R, R), dyc[i % NB], stride=st, padding=pad))
+        print(json.dumps(row), flush=True)
+        res.append(row)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/bench_conv.json", "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
