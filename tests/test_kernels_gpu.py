@@ -174,17 +174,20 @@ def test_bn_act_fwd_bwd_matches_autograd(C, relu):
         t = F.batch_norm(xr.reshape(-1, C), None, None, gr, br, True, 0.1, 1e-5).reshape(N, H, W, C)
         if use_skip:
             t = t + sr
-        ref = torch.relu(t) if relu else t
-        assert rel_l2(y, ref) < 4e-3
+        # teacher-forced gate: the kernel rounds bn(x) and the sum to bf16 like the autocast
+        # reference does, so pre-activations within one bf16 ulp of zero may gate differently from
+        # this fp32 restatement; use the kernel's own gate for the gradient comparison.
+        gate = (y != 0).float()
+        ref = t * gate if relu else t
+        assert rel_l2(y, torch.relu(t) if relu else t) < 4e-3
         ref.backward(dy.float())
         dx, dgamma, dbeta, dskip = ops.bn_act_bwd(dy, y, x, mean, invstd, gamma, relu=relu,
                                                   want_dskip=use_skip)
-        # the kernel masks with ITS OWN y; near-zero pre-activations may flip: compare in bulk norms
-        assert rel_l2(dx, xr.grad) < 2e-2
-        assert rel_l2(dgamma, gr.grad) < 2e-2
-        assert rel_l2(dbeta, br.grad) < 2e-2
+        assert rel_l2(dx, xr.grad) < 6e-3
+        assert rel_l2(dgamma, gr.grad) < 2e-3
+        assert rel_l2(dbeta, br.grad) < 2e-3
         if use_skip:
-            assert rel_l2(dskip, sr.grad) < 2e-2
+            assert rel_l2(dskip, sr.grad) < 4e-3
 
 
 def test_bn_act_eval_mode_and_subsample_pad_skip():
@@ -241,19 +244,20 @@ def test_subsample_upsample():
 def test_pools(k, s, p, H):
     ops, _ = _ops()
     x = torch.randn(2, H, H, 32, device="cuda").bfloat16()
-    xa = nhwc(x).float().requires_grad_(True)
+    # NCHW-contiguous reference tensors (torch's channels_last avg_pool2d backward differs)
+    xa = nhwc(x).float().contiguous().requires_grad_(True)
     ref = F.avg_pool2d(xa, k, s, p)
     y = ops.avgpool_fwd(x, k, s, p)
     assert rel_l2(nhwc(y), ref) < 4e-3
     dy = torch.randn_like(y)
-    ref.backward(nhwc(dy).float())
+    ref.backward(nhwc(dy).float().contiguous())
     dx = ops.avgpool_bwd(dy, tuple(x.shape), k, s, p)
     assert rel_l2(nhwc(dx), xa.grad) < 8e-3
-    xm = nhwc(x).float().requires_grad_(True)
+    xm = nhwc(x).float().contiguous().requires_grad_(True)
     refm = F.max_pool2d(xm, k, s, p)
     ym = ops.maxpool_fwd(x, k, s, p)
     assert torch.equal(nhwc(ym).float(), refm)
-    refm.backward(nhwc(dy).float())
+    refm.backward(nhwc(dy).float().contiguous())
     dxm = ops.maxpool_bwd(dy, x, ym, k, s, p)
     assert rel_l2(nhwc(dxm), xm.grad) < 4e-3
 
