@@ -120,8 +120,8 @@ int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void
 /* y[n,h,w,c] = x[n,2h,2w,c] (AvgPool2d(kernel 1, stride 2), residual_block.py:49,90,151,206). */
 int b200_subsample2(const void* x, void* y, int N, int H, int W, int C, b200_stream_t stream);
 /* dx[n,2h,2w,c] += g[n,h,w,c] for c < Cg (backward of subsample (+ zero channel pad)); dx is
- * [N,2H,2W,C] with C >= Cg, g is [N,H,W,Cg]. */
-int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg,
+ * [N,2H,2W,C] with C >= Cg, g is [N,H,W,ldg] (channel pitch ldg >= Cg; only the first Cg are used). */
+int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg, int ldg,
                       b200_stream_t stream);
 
 /* ---- pooling (resnet.py:77-87) ------------------------------------------------------------- */

@@ -39,7 +39,7 @@ SIGNATURES = {
     "b200_bn_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int,
                                 c_float, c_uint64, _P, c_size_t, _P]),
     "b200_subsample2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
-    "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_avgpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
     "b200_avgpool_bwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
     "b200_maxpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),

@@ -1,0 +1,33 @@
+"""Evaluation loop (reference: resnet/algos/evaluation.py:14-42): eval-mode forward over the test
+loader (BN from running statistics, dropout off), per-batch metric means, global mean over ranks.
+Metrics stay on the device until the single host read at the end."""
+from typing import Any, Dict
+
+import torch as tc
+
+from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics, global_means
+
+
+@tc.no_grad()
+def evaluation_loop(world_size: int, device, dl_test, classifier, **kwargs: Dict[str, Any]) -> Dict[str, float]:
+    """
+    Evaluates classifier on the validation/test set.
+
+    :param world_size: World size.
+    :param device: Device.
+    :param dl_test: Test/val dataloader.
+    :param classifier: Classifier.
+    :return: Dictionary of global metric floats, keyed by name.
+    """
+    classifier.eval()
+    sums, num_batch = None, 0
+    for x, y in dl_test:
+        x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+        m = compute_losses_and_metrics(logits=classifier(x), labels=y)
+        vec = tc.stack([m["loss"].float(), m["top1_err"].float(), m["top5_err"].float()])
+        sums = vec if sums is None else sums + vec
+        num_batch += 1
+    if num_batch == 0:
+        return {}
+    sums = sums / num_batch
+    return global_means({"loss": sums[0], "top1_err": sums[1], "top5_err": sums[2]}, world_size)

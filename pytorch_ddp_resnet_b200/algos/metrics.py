@@ -1,0 +1,69 @@
+"""
+Loss and metrics (reference: resnet/algos/metrics.py:10-41). Cross entropy (mean), top-1 and top-5
+error come out of ONE kernel launch; the backward pass is a second launch of the same kernel that
+writes d(loss)/d(logits).
+"""
+from collections import Counter
+
+import torch as tc
+
+from pytorch_ddp_resnet_b200 import ops
+from pytorch_ddp_resnet_b200._lib import B200Error
+
+
+class _CeTopKFn(tc.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        if not logits.is_cuda:
+            raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        lg = logits if (logits.dtype == tc.bfloat16 and logits.is_contiguous()) else logits.to(tc.bfloat16).contiguous()
+        out, _ = ops.ce_topk(lg, labels.contiguous(), want_metrics=True)
+        ctx.save_for_backward(lg, labels)
+        ctx.in_dtype = logits.dtype
+        loss, top1, top5 = out[0], out[1], out[2]
+        ctx.mark_non_differentiable(top1, top5)
+        return loss, top1, top5
+
+    @staticmethod
+    def backward(ctx, gloss, _g1, _g5):
+        lg, labels = ctx.saved_tensors
+        scale = gloss.to(tc.float32).contiguous()
+        _, dl = ops.ce_topk(lg, labels.contiguous(), want_metrics=False, want_dlogits=True, grad_scale=scale)
+        return dl.to(ctx.in_dtype), None
+
+
+def cross_entropy_loss(logits, labels):
+    return _CeTopKFn.apply(logits, labels)[0]
+
+
+def top_k_err(logits, labels, k):
+    if k not in (1, 5):
+        raise ValueError("the fused metric kernel reports top-1 and top-5 error")
+    return _CeTopKFn.apply(logits, labels)[1 if k == 1 else 2]
+
+
+def compute_losses_and_metrics(logits, labels):
+    loss, top1_err, top5_err = _CeTopKFn.apply(logits, labels)
+    return {
+        "loss": loss,
+        "top1_err": top1_err,
+        "top5_err": top5_err
+    }
+
+
+def global_mean(metric, world_size):
+    # for logging purposes only!
+    global_metric = metric.clone().float().detach()
+    tc.distributed.all_reduce(global_metric, op=tc.distributed.ReduceOp.SUM)
+    return global_metric.item() / world_size
+
+
+def global_means(metrics, world_size):
+    """One all-reduce and one host read for all metrics (the reference does one of each per metric,
+    metrics.py:32-41); same values."""
+    names = list(metrics)
+    packed = tc.stack([metrics[k].detach().float().reshape(()) for k in names])
+    if tc.distributed.is_available() and tc.distributed.is_initialized():
+        tc.distributed.all_reduce(packed, op=tc.distributed.ReduceOp.SUM)
+    vals = (packed / world_size).tolist()
+    return Counter(dict(zip(names, vals)))

@@ -1,0 +1,312 @@
+"""
+Parameter-holding leaf modules and the autograd Functions of the top-level spec tokens.
+
+The modules keep the reference's parameter / buffer names and logical shapes (so state_dicts are
+interchangeable with lucaslingle/pytorch_ddp_resnet: resnet/architectures/resnet.py:69-120) but none
+of them computes with ATen: their forward passes launch kernels from libb200resnet.so through
+pytorch_ddp_resnet_b200.ops. Activations travel between modules as bf16 tensors of logical shape
+[N, C, H, W] in channels_last memory format (physically NHWC, the layout the kernels use); conv
+filters are fp32 [O, I, kh, kw] parameters in channels_last format (physically KRSC).
+"""
+import math
+from typing import Optional
+
+import torch
+import torch as tc
+
+from pytorch_ddp_resnet_b200 import ops
+from pytorch_ddp_resnet_b200._lib import B200Error
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# --------------------------------------------------------------------------------------------------
+# layout helpers
+# --------------------------------------------------------------------------------------------------
+def as_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical-NCHW activation -> contiguous NHWC bf16 tensor (zero-copy on the fast path)."""
+    if x.dim() != 4:
+        raise B200Error(f"expected a 4-d activation, got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    v = x.permute(0, 2, 3, 1)
+    if x.dtype == torch.bfloat16 and v.is_contiguous():
+        return v
+    if x.dtype == torch.float32 and x.is_contiguous():
+        return ops.nchw_f32_to_nhwc_bf16(x)
+    return v.to(torch.bfloat16).contiguous()
+
+
+def as_nchw_view(x_nhwc: torch.Tensor) -> torch.Tensor:
+    """NHWC tensor -> logical NCHW view (channels_last strides)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def grad_nhwc(g: torch.Tensor) -> torch.Tensor:
+    """Incoming gradient of a logical-NCHW activation -> contiguous NHWC bf16."""
+    v = g.permute(0, 2, 3, 1)
+    if g.dtype == torch.bfloat16 and v.is_contiguous():
+        return v
+    return v.to(torch.bfloat16).contiguous()
+
+
+_dropout_counter = [0]
+
+
+def next_dropout_seed() -> int:
+    """Seeds of the counter-based dropout RNG: torch's global seed mixed with a call counter."""
+    _dropout_counter[0] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_counter[0] * 0xD1B54A32D192ED03) % (1 << 64)
+
+
+def reset_dropout_counter(value: int = 0) -> None:
+    _dropout_counter[0] = value
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter holders
+# --------------------------------------------------------------------------------------------------
+class Conv2d(tc.nn.Module):
+    """Holds `weight` [O, I, k, k] (channels_last => KRSC in memory) and an optional `bias` [O]."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int, padding: int,
+                 bias: bool):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        tc.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        self.weight = tc.nn.Parameter(w.contiguous(memory_format=torch.channels_last))
+        if bias:
+            bound = 1.0 / math.sqrt(in_channels * kernel_size * kernel_size)
+            self.bias = tc.nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+        self._cache = None
+
+    def _apply(self, fn, recurse=True):
+        # keep the KRSC physical layout across .to()/.cuda()/.float() (1x1 filters are ambiguous)
+        super()._apply(fn, recurse)
+        w = self.weight
+        if not w.data.permute(0, 2, 3, 1).is_contiguous():
+            w.data = w.data.contiguous(memory_format=torch.channels_last)
+        self._cache = None
+        return self
+
+    def krsc(self) -> torch.Tensor:
+        """fp32 [K, R, S, C] view of the master weight."""
+        v = self.weight.permute(0, 2, 3, 1)
+        if not v.is_contiguous():  # e.g. after load_state_dict into a re-strided tensor
+            with torch.no_grad():
+                self.weight.data = self.weight.data.contiguous(memory_format=torch.channels_last)
+            v = self.weight.permute(0, 2, 3, 1)
+            if not v.is_contiguous():  # 1x1 filters: strides are ambiguous, memory already is [K,1,1,C]
+                v = self.weight.detach().reshape(self.out_channels, self.in_channels)[:, None, None, :]
+        return v.detach()
+
+    def working_copies(self):
+        """(bf16 KRSC, bf16 CRSK), re-made only when the master weight changed."""
+        w = self.weight
+        key = (w.data_ptr(), w._version)
+        if self._cache is None or self._cache[0] != key:
+            wk, wt = ops.weight_prep(self.krsc().contiguous())
+            self._cache = (key, wk, wt)
+        return self._cache[1], self._cache[2]
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
+                f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
+
+
+def conv_weight_grad(dw_krsc: torch.Tensor) -> torch.Tensor:
+    """fp32 [K,R,S,C] kernel output -> gradient shaped like the [O,I,kh,kw] channels_last parameter."""
+    return dw_krsc.permute(0, 3, 1, 2)
+
+
+class BatchNorm2d(tc.nn.Module):
+    """weight/bias/running_mean/running_var/num_batches_tracked as torch.nn.BatchNorm2d."""
+
+    def __init__(self, num_features: int):
+        super().__init__()
+        self.num_features = num_features
+        self.eps, self.momentum = BN_EPS, BN_MOMENTUM
+        self.weight = tc.nn.Parameter(torch.ones(num_features))
+        self.bias = tc.nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def batch_stats(self, x_nhwc):
+        """Training statistics of x (+ in-place running-stat update)."""
+        return ops.bn_stats(x_nhwc, self.eps, self.momentum, self.running_mean, self.running_var,
+                            self.num_batches_tracked)
+
+    def forward(self, x):
+        return BnActFn.apply(x, self.weight, self.bias, self, False)
+
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}"
+
+
+class ReLU(tc.nn.Module):
+    def forward(self, x):
+        return BnActFn.apply(x, None, None, None, True)
+
+
+class Dropout(tc.nn.Module):
+    """Placeholder with the reference's attribute; the blocks fuse dropout into the BN kernels."""
+
+    def __init__(self, p: float):
+        super().__init__()
+        self.p = p
+
+    def extra_repr(self):
+        return f"p={self.p}"
+
+
+class Linear(tc.nn.Module):
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = tc.nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = tc.nn.Parameter(torch.empty(out_features))
+        tc.nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(in_features)
+        tc.nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x):
+        return LinearFn.apply(x, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f"{self.in_features}, {self.out_features}"
+
+
+class AvgPool2d(tc.nn.Module):
+    def __init__(self, kernel_size: int, stride: int, padding: int):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+
+    def forward(self, x):
+        return PoolFn.apply(x, self.kernel_size, self.stride, self.padding, False)
+
+
+class MaxPool2d(tc.nn.Module):
+    def __init__(self, kernel_size: int, stride: int, padding: int):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+
+    def forward(self, x):
+        return PoolFn.apply(x, self.kernel_size, self.stride, self.padding, True)
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd Functions of the top-level tokens
+# --------------------------------------------------------------------------------------------------
+class TopConvFn(torch.autograd.Function):
+    """`cI,O,K,S,P` token: conv with bias (resnet.py:69-75). The 3-channel stem takes the direct path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod: Conv2d):
+        xh = as_nhwc(x)
+        wk, wt = mod.working_copies()
+        y = ops.conv_fprop(xh, wk, mod.stride, mod.padding, bias=bias)
+        ctx.mod = mod
+        ctx.need_dx = x.requires_grad
+        ctx.x_dtype, ctx.x_cl = x.dtype, x.permute(0, 2, 3, 1).is_contiguous()
+        ctx.save_for_backward(xh, wt)
+        return as_nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, wt = ctx.saved_tensors
+        mod = ctx.mod
+        g = grad_nhwc(gy)
+        k = mod.kernel_size
+        dw, db = ops.conv_wgrad(g, xh, k, k, mod.stride, mod.padding, want_dbias=mod.bias is not None)
+        dx = None
+        if ctx.need_dx:
+            d = ops.conv_dgrad(g, wt, (xh.shape[1], xh.shape[2]), mod.stride, mod.padding)
+            dx = as_nchw_view(d)
+            if ctx.x_dtype != torch.bfloat16 or not ctx.x_cl:
+                dx = dx.to(ctx.x_dtype).contiguous()
+        return dx, conv_weight_grad(dw), db, None
+
+
+class BnActFn(torch.autograd.Function):
+    """Top-level `n`, `a` and fused `n a` tokens (resnet.py:111-115)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn: Optional[BatchNorm2d], relu: bool):
+        xh = as_nhwc(x)
+        ctx.relu, ctx.affine, ctx.train = relu, bn is not None, bn is not None and bn.training
+        if bn is None:
+            y = ops.bn_act_fwd(xh, relu=relu)
+            ctx.save_for_backward(y)
+        elif bn.training:
+            mean, invstd = bn.batch_stats(xh)
+            y = ops.bn_act_fwd(xh, mean, invstd, gamma, beta, relu=relu)
+            ctx.save_for_backward(xh, y, mean, invstd, gamma)
+        else:
+            y = ops.bn_act_fwd(xh, bn.running_mean, bn.running_var, gamma, beta, stat_is_var=True,
+                               eps=bn.eps, relu=relu)
+        return as_nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        g = grad_nhwc(gy)
+        if not ctx.affine:
+            (y,) = ctx.saved_tensors
+            dx, _, _, _ = ops.bn_act_bwd(g, y, None, relu=ctx.relu)
+            return as_nchw_view(dx), None, None, None, None
+        if not ctx.train:
+            raise B200Error("backward through eval-mode BatchNorm is not supported")
+        xh, y, mean, invstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta, _ = ops.bn_act_bwd(g, y, xh, mean, invstd, gamma, relu=ctx.relu)
+        return as_nchw_view(dx), dgamma, dbeta, None, None
+
+
+class PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k: int, stride: int, pad: int, is_max: bool):
+        xh = as_nhwc(x)
+        y = ops.maxpool_fwd(xh, k, stride, pad) if is_max else ops.avgpool_fwd(xh, k, stride, pad)
+        ctx.cfg = (k, stride, pad, is_max, tuple(xh.shape))
+        if is_max:
+            ctx.save_for_backward(xh, y)
+        return as_nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, stride, pad, is_max, shape = ctx.cfg
+        g = grad_nhwc(gy)
+        if is_max:
+            xh, y = ctx.saved_tensors
+            dx = ops.maxpool_bwd(g, xh, y, k, stride, pad)
+        else:
+            dx = ops.avgpool_bwd(g, shape, k, stride, pad)
+        return as_nchw_view(dx), None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """`fI,O` token after Flatten (resnet.py:117-120): bf16 logits, fp32 parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if not x.is_cuda:
+            raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        x2 = x if (x.dtype == torch.bfloat16 and x.is_contiguous()) else x.to(torch.bfloat16).contiguous()
+        y = ops.linear_fwd(x2, weight, bias)
+        ctx.need_dx = x.requires_grad
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x2, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight = ctx.saved_tensors
+        g = gy if (gy.dtype == torch.bfloat16 and gy.is_contiguous()) else gy.to(torch.bfloat16).contiguous()
+        dx, dw, db = ops.linear_bwd(g, x2, weight, want_dx=ctx.need_dx)
+        if dx is not None and ctx.x_dtype != torch.bfloat16:
+            dx = dx.to(ctx.x_dtype)
+        return dx, dw, db

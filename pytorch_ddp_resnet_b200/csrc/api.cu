@@ -677,11 +677,12 @@ extern "C" int b200_subsample2(const void* x, void* y, int N, int H, int W, int 
   return 0;
 }
 
-extern "C" int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg,
+extern "C" int b200_upsample_add(void* dx, const void* g, int N, int H, int W, int C, int Cg, int ldg,
                                  b200_stream_t stream) {
-  B200_REQUIRE(dx && g && C % 8 == 0 && Cg % 8 == 0 && Cg <= C, "upsample_add: bad arguments");
+  B200_REQUIRE(dx && g && C % 8 == 0 && Cg % 8 == 0 && Cg <= C && ldg >= Cg && ldg % 8 == 0,
+               "upsample_add: bad arguments");
   upsample_add_kernel<<<ew_grid((size_t)N * H * W * Cg / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (bf16*)dx, (const bf16*)g, N, H, W, C, Cg);
+      (bf16*)dx, (const bf16*)g, N, H, W, C, Cg, ldg);
   B200_LAUNCH_CHECK("upsample_add_kernel");
   return 0;
 }

@@ -372,9 +372,9 @@ __global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__
   }
 }
 
-// dx[n,2h,2w,c] = bf16(dx + g[n,h,w,c]) for c < Cg
+// dx[n,2h,2w,c] = bf16(dx + g[n,h,w,c]) for c < Cg; g has channel pitch ldg >= Cg
 __global__ void upsample_add_kernel(bf16* __restrict__ dx, const bf16* __restrict__ g, int N, int H,
-                                    int W, int C, int Cg) {
+                                    int W, int C, int Cg, int ldg) {
   const int CGg = Cg / 8;
   const size_t nvec = (size_t)N * H * W * CGg;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
@@ -388,7 +388,7 @@ __global__ void upsample_add_kernel(bf16* __restrict__ dx, const bf16* __restric
     bf16* dp = dx + dpix * C + (size_t)cg * 8;
     Vec8 a, b;
     a.raw = *reinterpret_cast<const uint4*>(dp);
-    b.raw = ldg_stream(g + v * 8);
+    b.raw = ldg_stream(g + pix * ldg + (size_t)cg * 8);
     float fa[8], fb[8];
     a.to_float(fa);
     b.to_float(fb);

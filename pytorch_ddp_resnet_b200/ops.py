@@ -205,13 +205,14 @@ def subsample2(x):
     return y
 
 
-def upsample_add_(dx, g):
-    """dx[n, 2h, 2w, :Cg] += g[n, h, w, :] in place."""
+def upsample_add_(dx, g, Cg: Optional[int] = None):
+    """dx[n, 2h, 2w, :Cg] += g[n, h, w, :Cg] in place (Cg defaults to all channels of g)."""
     _check_act(dx, "upsample_add.dx")
     _check_act(g, "upsample_add.g")
-    N, H, W, Cg = g.shape
+    N, H, W, ldg = g.shape
+    Cg = ldg if Cg is None else Cg
     assert dx.shape[0] == N and dx.shape[1] == 2 * H and dx.shape[2] == 2 * W and dx.shape[3] >= Cg
-    _lib.call("b200_upsample_add", dx.data_ptr(), g.data_ptr(), N, H, W, dx.shape[3], Cg, _stream())
+    _lib.call("b200_upsample_add", dx.data_ptr(), g.data_ptr(), N, H, W, dx.shape[3], Cg, ldg, _stream())
     return dx
 
 
