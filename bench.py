@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""
+bench.py — train img/s of WRN-28-10 (dropout 0.3) on CIFAR-shaped synthetic data, batch 128 per GPU,
+bf16, N GPUs of one node (BASELINE.json configs[1]; N > 1 is the DDP weak-scaling run of configs[4]).
+
+    python bench.py --gpus 1 --steps 30 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's algorithm on the host CPU cores
+
+One "step" = forward + mean cross-entropy + backward (+ bucketed NCCL gradient all-reduce through
+DistributedDataParallel) + fused SGD update through the public API of pytorch_ddp_resnet_b200.
+`value`  : images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same step fed from pinned host memory (H2D copy of x, y every step) with a device->host
+           read of the loss every step, inside the timed region.
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv, fprop of the 160->160 3x3 @32x32 layer
+           that carries 34.6 % of the FLOPs) timed alone with CUDA events, against the measured
+           bf16 peak in MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle (a port of the reference's algorithm to plain torch fp32 ops) timed on the
+           box's host cores on a bounded sample (reported baseline only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SPEC = "c3,160,3,1,1 r4 r4 r4 n a ap8,1,0 fc640,10"
+PREACT, USE_PROJ, DROPOUT = True, True, 0.3
+BATCH_PER_GPU = 128
+SGD = dict(lr=0.1, momentum=0.9, dampening=0.0, nesterov=True, weight_decay=5e-4)
+WORKLOAD = "WRN-28-10 (dropout 0.3) CIFAR-10-shape 32x32 synthetic bf16 training, batch 128/GPU"
+METRIC = "train img/s WRN-28-10 CIFAR"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16=p.get("bf16_tflops", 1590.0), bf16_sustained=p.get("bf16_tflops_sustained", 1400.0),
+                    hbm=p.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        busy = sm[len(sm) // 2:] if sm else []  # upper half = samples under load
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_steps(batch: int, steps: int, warmup: int):
+    """img/s of the oracle training step (WRN-28-10, fp32, all host threads) on a bounded sample."""
+    import torch
+    from oracle import resnet_oracle as O
+    state = O.init_state(SPEC, PREACT, USE_PROJ, seed=0)
+    bufs = {}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (batch,), generator=g)
+    for _ in range(warmup):
+        O.train_step(state, bufs, x, y, SPEC, PREACT, USE_PROJ, DROPOUT, dict(SGD))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(state, bufs, x, y, SPEC, PREACT, USE_PROJ, DROPOUT, dict(SGD))
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    batch = 16
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 1))
+    ips, spstep = cpu_steps(batch, steps, warm)
+    sample = f"{steps} steps (+{warm} warm-up) of batch {batch} of the same WRN-28-10 workload, fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def time_dominant_kernel(torch, ops, _lib, iters=30):
+    """Average duration of the dominant kernel launch (conv fprop 160->160 3x3 @32x32, batch 128),
+    CUDA events on the launching stream, rotating inputs whose total footprint exceeds L2."""
+    N, H, W, C, K = BATCH_PER_GPU, 32, 32, 160, 160
+    nb = 6  # 6 x (42 MB in + 42 MB out) > 126 MB L2
+    xs = [torch.randn(N, H, W, C, device="cuda").bfloat16() for _ in range(nb)]
+    w = (torch.randn(K, 3, 3, C, device="cuda") * 0.02).bfloat16()
+    for i in range(3):
+        ops.conv_fprop(xs[i % nb], w, 1, 1, algo=_lib.ALGO_TC)
+    # capture the launches in a CUDA graph so that host launch latency is not part of the number
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.conv_fprop(xs[0], w, 1, 1, algo=_lib.ALGO_TC)
+        with torch.cuda.graph(g, stream=s):
+            for i in range(iters):
+                ops.conv_fprop(xs[i % nb], w, 1, 1, algo=_lib.ALGO_TC)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * N * H * W * K * C * 9
+    return ms, flops
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pytorch_ddp_resnet_b200 import _lib, ops
+    from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    _lib.load()
+
+    torch.manual_seed(0)
+    model = ResNet(SPEC, PREACT, USE_PROJ, DROPOUT).to(device).train()
+    if world > 1:
+        classifier = torch.nn.parallel.DistributedDataParallel(
+            model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    else:
+        classifier = model
+    opt = get_optimizer("SGD", classifier, dict(SGD))
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 4
+    xs_host = [torch.randn(BATCH_PER_GPU, 3, 32, 32, generator=gen).pin_memory() for _ in range(nbuf)]
+    ys_host = [torch.randint(0, 10, (BATCH_PER_GPU,), generator=gen).pin_memory() for _ in range(nbuf)]
+    xs_dev = [x.to(device) for x in xs_host]
+    ys_dev = [y.to(device) for y in ys_host]
+
+    def step(x, y):
+        m = compute_losses_and_metrics(logits=classifier(x), labels=y)
+        m["loss"].backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return m["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_steps, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(run_steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident run ---------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(xs_dev[i % nbuf], ys_dev[i % nbuf])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    total_ms = timed(args.steps, lambda i: step(xs_dev[i % nbuf], ys_dev[i % nbuf]))
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = BATCH_PER_GPU * world * args.steps / (total_ms / 1e3)
+
+    # ---- end to end: pinned host batch -> H2D, step, loss -> host, every step --------------------
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+
+    def e2e_step(i):
+        x = xs_host[i % nbuf].to(device, non_blocking=True)
+        y = ys_host[i % nbuf].to(device, non_blocking=True)
+        loss = step(x, y)
+        loss_host[i % nbuf].copy_(loss.detach().float(), non_blocking=True)
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    e2e_ms = timed(args.steps, e2e_step)
+    e2e_value = BATCH_PER_GPU * world * args.steps / (e2e_ms / 1e3)
+    last_loss = float(loss_host[(args.steps - 1) % nbuf].item())
+    h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 8
+    d2h = 4
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + CPU baseline (rank 0) ---------------------------------
+    pk = peaks()
+    kms, kflops = time_dominant_kernel(torch, ops, _lib)
+    achieved = kflops / (kms * 1e-3) / 1e12
+    from oracle import resnet_oracle as O
+    _, train_flops = O.conv_train_flops(SPEC, PREACT, USE_PROJ, BATCH_PER_GPU, 32)
+    conv_tflops_in_step = train_flops / (ms_per_step * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (~3 GB of saved activations) is far larger than the 126 MB L2; "
+                         "4 rotating input batches"},
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / args.steps, "last_loss": last_loss},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16"], "traffic": None,
+                     "kernel": "conv_tc_kernel<32> fprop 3x3 s1 160->160 @32x32 batch 128 (60.4 GFLOP/launch)",
+                     "kernel_ms": kms, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
+                     "step_conv_tflops": conv_tflops_in_step,
+                     "step_conv_frac_of_sustained": conv_tflops_in_step / pk["bf16_sustained"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        ips, _ = cpu_steps(8, 2, 1)
+        line["cpu_baseline"] = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+                                "sample": "2 steps (+1 warm-up) of batch 8 of the same WRN-28-10 workload, "
+                                          f"fp32 oracle, {cores} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,8 @@ enum {
 /* ---- library ------------------------------------------------------------------------------- */
 int b200_version(void);
 const char* b200_last_error(void);
+/* Number of kernels this library has launched in the calling process so far. */
+long long b200_launch_count(void);
 /* 0 iff the current CUDA device is compute capability 10.x (sm_100a code is the only code here). */
 int b200_device_check(void);
 /* Returns 1 when the tcgen05 path supports the shape, else 0. Never fails. */

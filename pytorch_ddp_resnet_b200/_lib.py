@@ -7,7 +7,7 @@ host-side logic (spec parsing, state_dict layout, configs) can be tested without
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200resnet.so")
@@ -23,6 +23,7 @@ _CONV_DIMS = [c_int] * 9  # N H W C K R S stride pad
 SIGNATURES = {
     "b200_version": (c_int, []),
     "b200_last_error": (c_char_p, []),
+    "b200_launch_count": (c_longlong, []),
     "b200_device_check": (c_int, []),
     "b200_conv2d_tc_supported": (c_int, [c_int] + _CONV_DIMS),
     "b200_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
@@ -96,3 +97,8 @@ def require_device(device_index: int) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args), name)
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process so far."""
+    return int(load().b200_launch_count())

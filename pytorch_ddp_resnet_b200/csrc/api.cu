@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/b200resnet.h"
 #include "common.cuh"
@@ -41,8 +42,11 @@ static int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(2, "%s failed: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
 
+static std::atomic<long long> g_launches{0};
+
 #define B200_LAUNCH_CHECK(name)                                                          \
   do {                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) return fail(3, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)
@@ -66,6 +70,7 @@ static inline int ew_grid(size_t work_items, int per_block = EW_THREADS) {
 }
 
 extern "C" int b200_version(void) { return 100; }
+extern "C" long long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" const char* b200_last_error(void) { return g_err; }
 
 extern "C" int b200_device_check(void) {
