@@ -213,9 +213,31 @@ extern "C" int b200_conv2d_tc_supported(int pass, int N, int H, int W, int C, in
   return 1;
 }
 
+// Few-input-channel convolutions (the 3-channel stems) run as im2col (K padded to a multiple of 32)
+// followed by the tcgen05 GEMM path as a 1x1 convolution over Kpad channels.
+static int im2col_kpad(int R, int S, int C) { return ((R * S * C + 31) / 32) * 32; }
+
+static bool use_im2col(int algo, int pass, int N, int H, int W, int C, int K, int R, int S, int stride,
+                       int pad) {
+  if (algo == B200_ALGO_DIRECT || pass == B200_PASS_DGRAD) return false;
+  if (b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad)) return false;
+  if (C >= 16 || K % 16 != 0 || R * S * C > 1024) return false;
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (P < 1 || Q < 1) return false;
+  if (pass == B200_PASS_WGRAD && plan_tiles(N, P, Q).rows_valid % 16 != 0) return false;
+  return true;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 extern "C" size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int C, int K, int R,
                                               int S, int stride, int pad, int algo) {
   if (algo == B200_ALGO_DIRECT) return 0;
+  if (use_im2col(algo, pass, N, H, W, C, K, R, S, stride, pad)) {
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    const size_t kpad = im2col_kpad(R, S, C);
+    return align_up((size_t)N * P * Q * kpad * 2, 1024) + align_up((size_t)K * kpad * 4, 1024);
+  }
   if (stride != 2) return 0;
   if (!b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad)) return 0;
   return (size_t)N * H * W * C * 2;  // parity-split copy of the full-resolution tensor
@@ -310,6 +332,23 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
   B200_REQUIRE(P > 0 && Q > 0, "conv2d_fprop: empty output");
   cudaStream_t st = as_stream(stream);
   const bool tc = use_tc(algo, B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad);
+  if (!tc && use_im2col(algo, B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad)) {
+    const int kpad = im2col_kpad(R, S, C);
+    const size_t col_bytes = align_up((size_t)N * P * Q * kpad * 2, 1024);
+    B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 2, "conv2d_fprop: workspace too small");
+    bf16* col = reinterpret_cast<bf16*>(ws);
+    bf16* wpad = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(ws) + col_bytes);
+    im2col_kernel<<<ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st>>>(
+        (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
+    B200_LAUNCH_CHECK("im2col_kernel");
+    repitch_rows_kernel<bf16><<<ew_grid((size_t)K * kpad), EW_THREADS, 0, st>>>(
+        (const bf16*)w_krsc, wpad, K, R * S * C, kpad);
+    B200_LAUNCH_CHECK("repitch_rows_kernel");
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    tt.n = 1;
+    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st);
+  }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
@@ -449,6 +488,45 @@ static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, Wgra
   return 0;
 }
 
+// Shifted-window wgrad launch. act: [Nact][Ha][Wa][C] bf16, dy: [N][P][Q][K] bf16,
+// dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
+static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
+                        int Q, int K, const TapTable& taps, float* dw, cudaStream_t st) {
+  const int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
+  int BN = pick_bn(K, SL, 160);
+  B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
+  TilePlan t = plan_tiles(N, P, Q);
+  B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc: pixel tile of %d rows is not a multiple of 16",
+               t.rows_valid);
+  WgradTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bw = t.bw; a.bh = t.bh; a.bn = t.bn;
+  a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
+  a.num_ptiles = t.tiles_w * t.tiles_h * t.tiles_n;
+  a.kmmas = t.rows_valid / 16;
+  a.slabs_per_tap = C / SL;
+  a.nslabs_total = taps.n * a.slabs_per_tap;
+  const int spm = 128 / SL;
+  a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
+  a.BN = BN; a.n_ntiles = K / BN;
+  a.ktot = taps.n * C;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < BN) a.tmem_cols *= 2;
+  const int cols = a.n_mtiles * a.n_ntiles;
+  int splits = std::max(1, (2 * num_sms() + cols - 1) / cols);
+  splits = std::min(splits, a.num_ptiles);
+  const int per = (a.num_ptiles + splits - 1) / splits;
+  a.splits = (a.num_ptiles + per - 1) / per;
+  a.taps = taps;
+  a.dw = dw;
+  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
+  CUtensorMap tmX, tmDy;
+  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn)) return rc;
+  if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
+  if (SL == 32) return launch_wgrad_tc<32>(tmX, tmDy, a, st);
+  return launch_wgrad_tc<16>(tmX, tmDy, a, st);
+}
+
 extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N,
                                  int H, int W, int C, int K, int R, int S, int stride, int pad,
                                  int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
@@ -465,6 +543,24 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     B200_LAUNCH_CHECK("conv_dbias_kernel");
   }
   const bool tc = use_tc(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);
+  if (!tc && use_im2col(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad)) {
+    const int kpad = im2col_kpad(R, S, C);
+    const size_t col_bytes = align_up((size_t)N * P * Q * kpad * 2, 1024);
+    B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 4, "conv2d_wgrad: workspace too small");
+    bf16* col = reinterpret_cast<bf16*>(ws);
+    float* dwpad = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + col_bytes);
+    im2col_kernel<<<ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st>>>(
+        (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
+    B200_LAUNCH_CHECK("im2col_kernel");
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    tt.n = 1;
+    if (int rc = run_wgrad_tc(col, N, P, Q, kpad, dy, N, P, Q, K, tt, dwpad, st)) return rc;
+    repitch_rows_kernel<float><<<ew_grid((size_t)K * R * S * C), EW_THREADS, 0, st>>>(
+        dwpad, dw_krsc, K, kpad, R * S * C);
+    B200_LAUNCH_CHECK("repitch_rows_kernel");
+    return 0;
+  }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_wgrad: shape not supported by the tcgen05 path");
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
@@ -490,37 +586,8 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     B200_LAUNCH_CHECK("parity_kernel<split>");
     act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
   }
-  const int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
-  int BN = pick_bn(K, SL, 160);
-  B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
-  TilePlan t = plan_tiles(N, P, Q);
-  WgradTcArgs a;
-  memset(&a, 0, sizeof(a));
-  a.bw = t.bw; a.bh = t.bh; a.bn = t.bn;
-  a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
-  a.num_ptiles = t.tiles_w * t.tiles_h * t.tiles_n;
-  a.kmmas = t.rows_valid / 16;
-  a.slabs_per_tap = C / SL;
-  a.nslabs_total = R * S * a.slabs_per_tap;
-  const int spm = 128 / SL;
-  a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
-  a.BN = BN; a.n_ntiles = K / BN;
-  a.ktot = R * S * C;
-  a.tmem_cols = 32;
-  while (a.tmem_cols < BN) a.tmem_cols *= 2;
-  const int cols = a.n_mtiles * a.n_ntiles;
-  int splits = std::max(1, (2 * num_sms() + cols - 1) / cols);
-  splits = std::min(splits, a.num_ptiles);
-  const int per = (a.num_ptiles + splits - 1) / splits;
-  a.splits = (a.num_ptiles + per - 1) / per;
-  a.taps = fprop_taps(N, C, R, S, stride, pad);
-  a.dw = dw_krsc;
-  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)K * a.ktot * 4, st));
-  CUtensorMap tmX, tmDy;
-  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn)) return rc;
-  if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
-  if (SL == 32) return launch_wgrad_tc<32>(tmX, tmDy, a, st);
-  return launch_wgrad_tc<16>(tmX, tmDy, a, st);
+  TapTable tt = fprop_taps(N, C, R, S, stride, pad);
+  return run_wgrad_tc(act, Nact, Ha, Wa, C, dy, N, P, Q, K, tt, dw_krsc, st);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -583,7 +650,7 @@ extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, floa
   bn_stats_partial_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(
       (const bf16*)x, rows, C, (float*)ws);
   B200_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, nblk, rows, C, eps,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>((const float*)ws, nblk, rows, C, eps,
                                                             momentum, mean, invstd, running_mean,
                                                             running_var, num_batches_tracked);
   B200_LAUNCH_CHECK("bn_stats_finalize_kernel");
@@ -657,7 +724,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
     dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
     bn_act_bwd_reduce_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(a, (float*)ws);
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
     B200_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   }
   const size_t smem = a.affine ? (size_t)5 * C * sizeof(float) : 0;

@@ -84,20 +84,41 @@ bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* 
   block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, C, g.cg0 * 8);
 }
 
-// mean / invstd from the partials (+ running-stat update, torch.nn.BatchNorm2d semantics)
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t rows,
-                                         int C, float eps, float momentum, float* __restrict__ mean,
-                                         float* __restrict__ invstd, float* __restrict__ running_mean,
-                                         float* __restrict__ running_var,
-                                         int64_t* __restrict__ num_batches_tracked) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[((size_t)b * 2 + 0) * C + c];
-    ss += (double)partial[((size_t)b * 2 + 1) * C + c];
+// Sum of the per-block partials of two quantities for 32 channels per block: 8 row lanes stride over
+// the partial blocks (coalesced 128-byte reads), then a shared-memory tree over the lanes.
+constexpr int FIN_THREADS = 256;
+__device__ __forceinline__ bool finalize_sums(const float* __restrict__ partial, int nblk, int C,
+                                              int& c, double& s0, double& s1) {
+  __shared__ double red[2][8][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int k = lane; k < nblk; k += 8) {
+      a += (double)partial[((size_t)k * 2 + 0) * C + c];
+      b += (double)partial[((size_t)k * 2 + 1) * C + c];
+    }
   }
+  red[0][lane][cl] = a;
+  red[1][lane][cl] = b;
+  __syncthreads();
+  if (lane != 0 || c >= C) return false;
+  s0 = 0.0; s1 = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) { s0 += red[0][l][cl]; s1 += red[1][l][cl]; }
+  return true;
+}
+
+// mean / invstd from the partials (+ running-stat update, torch.nn.BatchNorm2d semantics)
+__global__ void __launch_bounds__(FIN_THREADS)
+bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t rows, int C, float eps,
+                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         int64_t* __restrict__ num_batches_tracked) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  int c;
+  double s, ss;
+  if (!finalize_sums(partial, nblk, C, c, s, ss)) return;
   const double m = s / (double)rows;
   double var = ss / (double)rows - m * m;
   if (var < 0.0) var = 0.0;
@@ -280,15 +301,12 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
                           g.cg0 * 8);
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[((size_t)b * 2 + 0) * C + c];
-    sx += (double)partial[((size_t)b * 2 + 1) * C + c];
-  }
+__global__ void __launch_bounds__(FIN_THREADS)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+  int c;
+  double s, sx;
+  if (!finalize_sums(partial, nblk, C, c, s, sx)) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)sx;
 }
@@ -456,6 +474,48 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, bf16* __res
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, k = k0 + threadIdx.x;
     if (k < K && c < C) wt[((size_t)c * RS + rs) * K + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// im2col for convolutions with very few input channels (the 3-channel stems): col[pix][kk] with
+// kk = (r*S + s)*C + c, zero padded to Kpad columns, so the conv becomes a 1x1 conv over Kpad channels
+// that the tcgen05 GEMM path can run. Also the matching zero-padding of filter rows.
+// -------------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W,
+                              int C, int R, int S, int stride, int pad, int P, int Q, int Kpad) {
+  const size_t total = (size_t)N * P * Q * Kpad;
+  const int rsc = R * S * C;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % Kpad);
+    const size_t pix = idx / Kpad;
+    float v = 0.f;
+    if (kk < rsc) {
+      const int c = kk % C;
+      const int s = (kk / C) % S;
+      const int r = kk / (C * S);
+      const int q = (int)(pix % Q);
+      const int p = (int)((pix / Q) % P);
+      const int n = (int)(pix / ((size_t)Q * P));
+      const int ih = p * stride + r - pad, iw = q * stride + s - pad;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+        v = __bfloat162float(x[(((size_t)n * H + ih) * W + iw) * C + c]);
+    }
+    col[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// dst[row][0..cols_dst) = src[row][0..cols_src) zero padded (cols_dst >= cols_src) or truncated
+template <typename T>
+__global__ void repitch_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows,
+                                    int cols_src, int cols_dst) {
+  const size_t total = (size_t)rows * cols_dst;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols_dst);
+    const size_t r = idx / cols_dst;
+    dst[idx] = (c < cols_src) ? src[r * cols_src + c] : T(0.f);
   }
 }
 

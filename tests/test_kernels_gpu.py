@@ -109,21 +109,29 @@ def test_conv_wgrad(shape, algo):
     assert rel_l2(db, dy.float().sum((0, 1, 2))) < 1e-3
 
 
-def test_stem_direct_conv():
+@pytest.mark.parametrize("algo", ["auto", "direct"])
+@pytest.mark.parametrize("geom", [(8, 32, 160, 3, 1, 1), (4, 32, 32, 7, 2, 3), (2, 224, 64, 7, 2, 3)])
+def test_stem_conv_few_input_channels(geom, algo):
+    """3-channel stems: 'auto' = im2col + tcgen05 GEMM, 'direct' = CUDA-core kernel."""
     ops, _lib = _ops()
-    x = torch.randn(8, 3, 32, 32, device="cuda")
-    w = torch.randn(160, 3, 3, 3, device="cuda") * 0.27
-    b = torch.randn(160, device="cuda") * 0.1
+    N, HW, K, R, stride, pad = geom
+    a = {"auto": _lib.ALGO_AUTO, "direct": _lib.ALGO_DIRECT}[algo]
+    x = torch.randn(N, 3, HW, HW, device="cuda")
+    w = torch.randn(K, 3, R, R, device="cuda") * (2.0 / (3 * R * R)) ** 0.5
+    b = torch.randn(K, device="cuda") * 0.1
     xh = ops.nchw_f32_to_nhwc_bf16(x)
     assert torch.equal(nhwc(xh), x.bfloat16())
     wk = w.permute(0, 2, 3, 1).contiguous().bfloat16()
-    y = ops.conv_fprop(xh, wk, 1, 1, bias=b)
-    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b.bfloat16().float(), padding=1)
+    y = ops.conv_fprop(xh, wk, stride, pad, bias=b, algo=a)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b.bfloat16().float(), stride=stride,
+                   padding=pad)
     assert rel_l2(nhwc(y), ref) < 4e-3
-    dy = torch.randn(8, 32, 32, 160, device="cuda").bfloat16()
-    dw, db = ops.conv_wgrad(dy, xh, 3, 3, 1, 1, want_dbias=True)
-    refw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (160, 3, 3, 3), nhwc(dy).float(), padding=1)
+    dy = torch.randn_like(y)
+    dw, db = ops.conv_wgrad(dy, xh, R, R, stride, pad, want_dbias=True, algo=a)
+    refw = torch.nn.grad.conv2d_weight(x.bfloat16().float(), (K, 3, R, R), nhwc(dy).float(),
+                                       stride=stride, padding=pad)
     assert rel_l2(dw.permute(0, 3, 1, 2), refw) < 1e-3
+    assert rel_l2(db, dy.float().sum((0, 1, 2))) < 1e-3
 
 
 def test_weight_prep():
