@@ -216,12 +216,21 @@ def run_ours(args):
     xs_dev = [x.to(device) for x in xs_host]
     ys_dev = [y.to(device) for y in ys_host]
 
-    def step(x, y):
-        m = compute_losses_and_metrics(logits=classifier(x), labels=y)
-        m["loss"].backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return m["loss"]
+    if args.eager:
+        def step(x, y):
+            m = compute_losses_and_metrics(logits=classifier(x), labels=y)
+            m["loss"].backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return m["loss"]
+    else:
+        # public API: whole-step CUDA-graph (pytorch_ddp_resnet_b200.utils.graph_util.GraphedTrainStep)
+        from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
+        graphed = GraphedTrainStep(classifier, opt, xs_dev[0], ys_dev[0])
+        launches_per_step = graphed.launches_per_step
+
+        def step(x, y):
+            return graphed(x, y)["loss"]
 
     def barrier():
         if world > 1:
@@ -250,6 +259,8 @@ def run_ours(args):
     l0 = _lib.launch_count()
     total_ms = timed(args.steps, lambda i: step(xs_dev[i % nbuf], ys_dev[i % nbuf]))
     launches = _lib.launch_count() - l0
+    if not args.eager:  # replays do not pass through the C ABI: count = kernels captured per step
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = BATCH_PER_GPU * world * args.steps / (total_ms / 1e3)
@@ -258,8 +269,11 @@ def run_ours(args):
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
 
     def e2e_step(i):
-        x = xs_host[i % nbuf].to(device, non_blocking=True)
-        y = ys_host[i % nbuf].to(device, non_blocking=True)
+        if args.eager:
+            x = xs_host[i % nbuf].to(device, non_blocking=True)
+            y = ys_host[i % nbuf].to(device, non_blocking=True)
+        else:  # GraphedTrainStep copies the pinned host batch into its static device buffers
+            x, y = xs_host[i % nbuf], ys_host[i % nbuf]
         loss = step(x, y)
         loss_host[i % nbuf].copy_(loss.detach().float(), non_blocking=True)
 
@@ -321,6 +335,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from the host (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

@@ -101,12 +101,14 @@ int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum,
 /* y = dropout( act( (x - mean) * invstd * gamma + beta [+ skip] ) ).
  * stat_is_var != 0: `invstd` holds a variance (eval mode, running stats) and rsqrt(var+eps) is applied.
  * gamma/beta/mean/invstd NULL  => the affine/normalise step is skipped (plain act/dropout/add).
- * relu: 0/1. dropout_p in [0,1): keep mask from the counter RNG keyed by (seed, element index).
+ * relu: 0/1. dropout_p in [0,1): keep mask from the counter RNG keyed by (seed, element index);
+ * seed_offset (device uint64 scalar, may be NULL) is a step counter folded into the seed on the
+ * device, so a captured CUDA graph draws a fresh mask at every replay (see b200_tick).
  * x is [N,H,W,C]; skip addressing per skip_mode (skip_C = channel count of the skip tensor). */
 int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const float* mean,
                     const float* invstd, int stat_is_var, float eps, const float* gamma,
                     const float* beta, const void* skip, int skip_mode, int skip_C, int relu,
-                    float dropout_p, uint64_t seed, b200_stream_t stream);
+                    float dropout_p, uint64_t seed, const uint64_t* seed_offset, b200_stream_t stream);
 
 /* Backward of b200_bn_act_fwd. y is the forward OUTPUT (its non-zero pattern is the relu mask; may
  * be NULL when relu == 0), x the forward input, dy the gradient w.r.t. y. The dropout mask is
@@ -117,7 +119,8 @@ int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const fl
 int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
                     const void* addend, int64_t rows, int C, const float* mean, const float* invstd,
                     const float* gamma, float* dgamma, float* dbeta, int relu, float dropout_p,
-                    uint64_t seed, void* ws, size_t ws_bytes, b200_stream_t stream);
+                    uint64_t seed, const uint64_t* seed_offset, void* ws, size_t ws_bytes,
+                    b200_stream_t stream);
 
 /* y[n,h,w,c] = x[n,2h,2w,c] (AvgPool2d(kernel 1, stride 2), residual_block.py:49,90,151,206). */
 int b200_subsample2(const void* x, void* y, int N, int H, int W, int C, b200_stream_t stream);
@@ -153,11 +156,16 @@ int b200_ce_topk(const void* logits, const int64_t* labels, float* out, void* dl
  * One launch for `n` tensors. Per element: g = grad (* inv_scale); g += wd * p;
  * buf = first_step ? g : momentum*buf + (1-dampening)*g; g = nesterov ? g + momentum*buf : buf;
  * p -= lr * g. If found_inf != NULL and *found_inf != 0 the step is skipped (GradScaler contract).
+ * lr_ptr (device fp32 scalar, may be NULL) overrides lr: schedulers can change it under a CUDA graph.
  * params/grads/bufs: device arrays of n device pointers; sizes: device array of n element counts. */
 int b200_sgd_step(float* const* params, const float* const* grads, float* const* bufs,
                   const int64_t* sizes, int n, int64_t max_size, float lr, float momentum,
                   float dampening, float weight_decay, int nesterov, int first_step,
-                  const float* inv_scale, const float* found_inf, b200_stream_t stream);
+                  const float* inv_scale, const float* found_inf, const float* lr_ptr,
+                  b200_stream_t stream);
+
+/* *counter += 1 on the device (one launch): the per-step tick of the dropout seed offset. */
+int b200_tick(uint64_t* counter, b200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,9 +36,9 @@ SIGNATURES = {
     "b200_bn_stats": (c_int, [_P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P,
                               c_size_t, _P]),
     "b200_bn_act_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_float, _P, _P,
-                                _P, c_int, c_int, c_int, c_float, c_uint64, _P]),
+                                _P, c_int, c_int, c_int, c_float, c_uint64, _P, _P]),
     "b200_bn_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int,
-                                c_float, c_uint64, _P, c_size_t, _P]),
+                                c_float, c_uint64, _P, _P, c_size_t, _P]),
     "b200_subsample2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_avgpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
@@ -49,7 +49,8 @@ SIGNATURES = {
     "b200_linear_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_ce_topk": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
     "b200_sgd_step": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float,
-                              c_int, c_int, _P, _P, _P]),
+                              c_int, c_int, _P, _P, _P, _P]),
+    "b200_tick": (c_int, [_P, _P]),
 }
 
 _lib = None

@@ -62,6 +62,9 @@ def training_loop(
 ) -> None:
     """Runs a training loop on a given process; see the reference docstring for the arguments."""
     writer = _make_writer(log_dir) if rank == 0 else None
+    # cuda_graph=True (config key, optional): capture the whole step once and replay it
+    use_graph = bool(kwargs.get("cuda_graph", False)) and scaler is None and num_microbatches == 1
+    graphed = None
     checkpointables = {
         'checkpoint_strategy': checkpoint_strategy,
         'classifier': classifier,
@@ -78,19 +81,25 @@ def training_loop(
         acc = Counter()
         for microbatch_id, (x, y) in enumerate(dl_train, 1):
             x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
-            metrics = compute_losses_and_metrics(logits=classifier(x), labels=y)
-            loss = metrics['loss']
-            (scaler.scale(loss) if scaler else loss).backward()
-            acc += global_means(metrics, world_size)
-
-            if microbatch_id % num_microbatches != 0:
-                continue
-            if scaler:
-                scaler.step(optimizer)
-                scaler.update()
+            if use_graph:
+                if graphed is None:
+                    from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
+                    graphed = GraphedTrainStep(classifier, optimizer, x, y)
+                acc += global_means(graphed(x, y), world_size)
             else:
-                optimizer.step()
-            optimizer.zero_grad(set_to_none=True)
+                metrics = compute_losses_and_metrics(logits=classifier(x), labels=y)
+                loss = metrics['loss']
+                (scaler.scale(loss) if scaler else loss).backward()
+                acc += global_means(metrics, world_size)
+
+                if microbatch_id % num_microbatches != 0:
+                    continue
+                if scaler:
+                    scaler.step(optimizer)
+                    scaler.update()
+                else:
+                    optimizer.step()
+                optimizer.zero_grad(set_to_none=True)
 
             logged = {k: v / num_microbatches for k, v in acc.items()}
             global_loss = logged.get('loss')

@@ -52,6 +52,14 @@ def grad_nhwc(g: torch.Tensor) -> torch.Tensor:
 
 
 _dropout_counter = [0]
+_weight_generation = [0]
+
+
+def invalidate_weight_caches() -> None:
+    """Marks every cached bf16 filter copy stale (parameters were changed behind torch's back, e.g. by
+    a CUDA-graph replay of the optimizer step)."""
+    _weight_generation[0] += 1
+
 
 
 def next_dropout_seed() -> int:
@@ -108,7 +116,7 @@ class Conv2d(tc.nn.Module):
     def working_copies(self):
         """(bf16 KRSC, bf16 CRSK), re-made only when the master weight changed."""
         w = self.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, _weight_generation[0])
         if self._cache is None or self._cache[0] != key:
             wk, wt = ops.weight_prep(self.krsc().contiguous())
             self._cache = (key, wk, wt)

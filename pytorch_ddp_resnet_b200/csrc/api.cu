@@ -667,7 +667,8 @@ static uint32_t drop_threshold(float p) {
 extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const float* mean,
                                const float* invstd, int stat_is_var, float eps, const float* gamma,
                                const float* beta, const void* skip, int skip_mode, int skip_C,
-                               int relu, float dropout_p, uint64_t seed, b200_stream_t stream) {
+                               int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                               b200_stream_t stream) {
   B200_REQUIRE(x && y, "bn_act_fwd: null pointer");
   B200_REQUIRE(C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
   B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "bn_act_fwd: dropout_p out of range");
@@ -685,6 +686,7 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   a.inv_keep = 1.f / (1.f - dropout_p);
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
+  a.seed_offset = seed_offset;
   const size_t smem = (size_t)2 * C * sizeof(float);
   static bool attr_set = false;
   if (smem > 48 * 1024 && !attr_set) {
@@ -701,8 +703,8 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
 extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
                                const void* addend, int64_t rows, int C, const float* mean,
                                const float* invstd, const float* gamma, float* dgamma, float* dbeta,
-                               int relu, float dropout_p, uint64_t seed, void* ws, size_t ws_bytes,
-                               b200_stream_t stream) {
+                               int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                               void* ws, size_t ws_bytes, b200_stream_t stream) {
   B200_REQUIRE(dy && dx, "bn_act_bwd: null pointer");
   B200_REQUIRE(C % 8 == 0, "bn_act_bwd: C=%d must be a multiple of 8", C);
   B200_REQUIRE(!relu || y, "bn_act_bwd: relu mask needs the forward output y");
@@ -716,6 +718,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
   a.inv_keep = 1.f / (1.f - dropout_p);
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
+  a.seed_offset = seed_offset;
   if (a.affine) {
     B200_REQUIRE(x && dgamma && dbeta && ws, "bn_act_bwd: null pointer (affine path)");
     B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_act_bwd: workspace too small");
@@ -856,13 +859,21 @@ extern "C" int b200_ce_topk(const void* logits, const int64_t* labels, float* ou
 extern "C" int b200_sgd_step(float* const* params, const float* const* grads, float* const* bufs,
                              const int64_t* sizes, int n, int64_t max_size, float lr, float momentum,
                              float dampening, float weight_decay, int nesterov, int first_step,
-                             const float* inv_scale, const float* found_inf, b200_stream_t stream) {
+                             const float* inv_scale, const float* found_inf, const float* lr_ptr,
+                             b200_stream_t stream) {
   B200_REQUIRE(params && grads && bufs && sizes && n > 0, "sgd_step: bad arguments");
   SgdArgs a{params, grads, bufs, sizes, lr, momentum, dampening, weight_decay,
-            nesterov, first_step, inv_scale, found_inf};
+            nesterov, first_step, inv_scale, found_inf, lr_ptr};
   const int64_t chunk = (int64_t)SGD_THREADS * SGD_VEC_PER_THREAD * 4;
   dim3 grid((unsigned)((max_size + chunk - 1) / chunk), n);
   sgd_step_kernel<<<grid, SGD_THREADS, 0, as_stream(stream)>>>(a);
   B200_LAUNCH_CHECK("sgd_step_kernel");
+  return 0;
+}
+
+extern "C" int b200_tick(uint64_t* counter, b200_stream_t stream) {
+  B200_REQUIRE(counter, "tick: null pointer");
+  tick_kernel<<<1, 1, 0, as_stream(stream)>>>(counter);
+  B200_LAUNCH_CHECK("tick_kernel");
   return 0;
 }

@@ -94,6 +94,12 @@ __host__ __device__ __forceinline__ uint32_t rng_draw(uint64_t seed, uint64_t id
   return mix32(mix32(lo ^ s0) + (hi ^ s1) * 0x9e3779b9U + 0x85ebca6bU);
 }
 
+// seed actually used by a launch: the host seed plus a device-resident step counter, so that a
+// captured CUDA graph draws fresh dropout masks at every replay
+__device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const uint64_t* seed_offset) {
+  return seed_offset ? seed + (*seed_offset) * 0x9E3779B97F4A7C15ull : seed;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

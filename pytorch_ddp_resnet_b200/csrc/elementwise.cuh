@@ -149,6 +149,7 @@ struct BnActFwdArgs {
   float inv_keep;
   uint32_t drop_thr;  // drop when u16 < drop_thr
   uint64_t seed;
+  const uint64_t* seed_offset;  // device step counter folded into the seed (CUDA-graph replays)
 };
 
 __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdArgs a) {
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdAr
   }
   const int CG = C / 8;
   const size_t nvec = (size_t)a.N * a.H * a.W * CG;
+  const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (size_t)gridDim.x * blockDim.x) {
     const int cg = (int)(v % CG);
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdAr
     if (a.drop_thr) {
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
-        const uint32_t d = rng_draw(a.seed, v * 4 + j2);
+        const uint32_t d = rng_draw(seed, v * 4 + j2);
         f[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2] * a.inv_keep);
         f[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2 + 1] * a.inv_keep);
       }
@@ -238,17 +240,18 @@ struct BnActBwdArgs {
   float inv_keep;
   uint32_t drop_thr;
   uint64_t seed;
+  const uint64_t* seed_offset;
 };
 
 // g = dy masked by relu (y != 0) and dropout (regenerated from the counter RNG), scaled by 1/(1-p)
-__device__ __forceinline__ void masked_grad(const BnActBwdArgs& a, size_t v, float* g) {
+__device__ __forceinline__ void masked_grad(const BnActBwdArgs& a, uint64_t seed, size_t v, float* g) {
   Vec8 dv;
   dv.raw = ldg_stream(a.dy + v * 8);
   dv.to_float(g);
   if (a.drop_thr) {
 #pragma unroll
     for (int j2 = 0; j2 < 4; ++j2) {
-      const uint32_t d = rng_draw(a.seed, v * 4 + j2);
+      const uint32_t d = rng_draw(seed, v * 4 + j2);
       g[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2] * a.inv_keep);
       g[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2 + 1] * a.inv_keep);
     }
@@ -271,6 +274,7 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   if (g.active) {
     const int cgi = g.cg0 + g.cgl;
     float mu[8], is[8];
@@ -285,7 +289,7 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
     for (int64_t r = r0 + g.rl; r < r1; r += g.RP) {
       const size_t v = (size_t)r * g.CG + cgi;
       float gr[8];
-      masked_grad(a, v, gr);
+      masked_grad(a, seed, v, gr);
       Vec8 xv;
       xv.raw = ldg_stream(a.x + v * 8);
       float xf[8];
@@ -328,11 +332,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_bwd_apply_kernel(const BnAc
   }
   const int CG = C / 8;
   const size_t nvec = (size_t)a.rows * CG;
+  const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += (size_t)gridDim.x * blockDim.x) {
     const int cg = (int)(v % CG);
     float g[8];
-    masked_grad(a, v, g);
+    masked_grad(a, seed, v, g);
     if (a.dskip) {
       Vec8 o;
       o.from_float(g);
@@ -368,6 +373,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_bwd_apply_kernel(const BnAc
     stg_stream(a.dx + v * 8, o.raw);
   }
 }
+
+__global__ void tick_kernel(uint64_t* counter) { *counter += 1; }
 
 // -------------------------------------------------------------------------------------------------
 // subsample / upsample-add / parity split and merge

@@ -109,19 +109,21 @@ struct SgdArgs {
   int nesterov, first_step;
   const float* inv_scale;
   const float* found_inf;
+  const float* lr_ptr;  // device-resident learning rate (overrides lr when non-null)
 };
 
 constexpr int SGD_THREADS = 256;
 constexpr int SGD_VEC_PER_THREAD = 4;
 
-__device__ __forceinline__ float sgd_one(float& p, float g, float& buf, const SgdArgs& a, float is) {
+__device__ __forceinline__ float sgd_one(float& p, float g, float& buf, const SgdArgs& a, float is,
+                                         float lr) {
   g *= is;
   g = fmaf(a.weight_decay, p, g);
   if (a.momentum != 0.f) {
     buf = a.first_step ? g : fmaf(a.momentum, buf, (1.f - a.dampening) * g);
     g = a.nesterov ? fmaf(a.momentum, buf, g) : buf;
   }
-  p = fmaf(-a.lr, g, p);
+  p = fmaf(-lr, g, p);
   return p;
 }
 
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(SGD_THREADS) sgd_step_kernel(const SgdArgs a) 
   const float* g = a.grads[t];
   float* m = a.bufs[t];
   const float is = a.inv_scale ? *a.inv_scale : 1.f;
+  const float lr = a.lr_ptr ? *a.lr_ptr : a.lr;
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
                          reinterpret_cast<uintptr_t>(m)) & 15) == 0;
 #pragma unroll
@@ -146,16 +149,16 @@ __global__ void __launch_bounds__(SGD_THREADS) sgd_step_kernel(const SgdArgs a) 
       float4 pv = *reinterpret_cast<float4*>(p + i);
       const float4 gv = *reinterpret_cast<const float4*>(g + i);
       float4 mv = a.first_step ? make_float4(0, 0, 0, 0) : *reinterpret_cast<float4*>(m + i);
-      sgd_one(pv.x, gv.x, mv.x, a, is);
-      sgd_one(pv.y, gv.y, mv.y, a, is);
-      sgd_one(pv.z, gv.z, mv.z, a, is);
-      sgd_one(pv.w, gv.w, mv.w, a, is);
+      sgd_one(pv.x, gv.x, mv.x, a, is, lr);
+      sgd_one(pv.y, gv.y, mv.y, a, is, lr);
+      sgd_one(pv.z, gv.z, mv.z, a, is, lr);
+      sgd_one(pv.w, gv.w, mv.w, a, is, lr);
       *reinterpret_cast<float4*>(p + i) = pv;
       if (a.momentum != 0.f) *reinterpret_cast<float4*>(m + i) = mv;
     } else {
       for (int64_t j = i; j < min(n, i + 4); ++j) {
         float pv = p[j], mv = a.first_step ? 0.f : m[j];
-        sgd_one(pv, g[j], mv, a, is);
+        sgd_one(pv, g[j], mv, a, is, lr);
         p[j] = pv;
         if (a.momentum != 0.f) m[j] = mv;
       }

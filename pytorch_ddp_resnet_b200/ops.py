@@ -16,6 +16,23 @@ from pytorch_ddp_resnet_b200 import _lib
 
 _ALGO_NAMES = {"auto": _lib.ALGO_AUTO, "direct": _lib.ALGO_DIRECT, "tc": _lib.ALGO_TC}
 _workspaces = {}
+_step_counters = {}
+
+
+def step_counter(device: torch.device) -> torch.Tensor:
+    """Per-device uint64 step counter (stored as int64) that the dropout kernels fold into their seed.
+    It only advances through tick(): a captured training step ticks it once per replay."""
+    t = _step_counters.get(device.index)
+    if t is None:
+        t = torch.zeros((), dtype=torch.int64, device=device)
+        _step_counters[device.index] = t
+    return t
+
+
+def tick(device: torch.device) -> None:
+    _lib.require_device(device.index or 0)
+    _lib.call("b200_tick", step_counter(device).data_ptr(), _stream())
+
 
 
 def conv_algo() -> int:
@@ -170,7 +187,8 @@ def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var:
             assert skip.shape[0] == N and skip.shape[1] == 2 * H and skip.shape[2] == 2 * W
     _lib.call("b200_bn_act_fwd", x.data_ptr(), y.data_ptr(), N, H, W, C, _p(mean), _p(invstd),
               int(stat_is_var), eps, _p(gamma), _p(beta), _p(skip), skip_mode if skip is not None else 0,
-              skip_C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+              skip_C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+              step_counter(x.device).data_ptr() if dropout_p > 0 else None, _stream())
     return y
 
 
@@ -192,7 +210,8 @@ def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = Tru
         assert addend.shape == dy.shape
     _lib.call("b200_bn_act_bwd", dy.data_ptr(), _p(y), _p(x), dx.data_ptr(), _p(dskip), _p(addend), rows,
               C, _p(mean), _p(invstd), _p(gamma), _p(dgamma), _p(dbeta), int(relu), float(dropout_p),
-              int(seed) & 0xFFFFFFFFFFFFFFFF, _p(ws), nws, _stream())
+              int(seed) & 0xFFFFFFFFFFFFFFFF,
+              step_counter(dy.device).data_ptr() if dropout_p > 0 else None, _p(ws), nws, _stream())
     return dx, dgamma, dbeta, dskip
 
 
@@ -293,7 +312,7 @@ def ce_topk(logits, labels, want_metrics=True, want_dlogits=False, grad_scale=No
 # optimizer
 # --------------------------------------------------------------------------------------------------
 def sgd_step(ptr_table: torch.Tensor, n: int, max_size: int, lr, momentum, dampening, weight_decay,
-             nesterov, first_step, inv_scale=None, found_inf=None):
+             nesterov, first_step, inv_scale=None, found_inf=None, lr_dev=None):
     """ptr_table: int64 CUDA tensor [4, n] = rows of param ptrs, grad ptrs, buf ptrs, sizes."""
     assert ptr_table.dtype == torch.int64 and ptr_table.is_cuda and ptr_table.shape == (4, n)
     _lib.require_device(ptr_table.device.index or 0)
@@ -301,4 +320,4 @@ def sgd_step(ptr_table: torch.Tensor, n: int, max_size: int, lr, momentum, dampe
     row = n * 8
     _lib.call("b200_sgd_step", base, base + row, base + 2 * row, base + 3 * row, n, max_size, float(lr),
               float(momentum), float(dampening), float(weight_decay), int(bool(nesterov)),
-              int(bool(first_step)), _p(inv_scale), _p(found_inf), _stream())
+              int(bool(first_step)), _p(inv_scale), _p(found_inf), _p(lr_dev), _stream())

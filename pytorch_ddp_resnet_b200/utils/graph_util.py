@@ -1,0 +1,85 @@
+"""
+Whole-step CUDA-graph capture: forward + loss/metrics + backward (+ DDP's bucketed NCCL all-reduce)
++ fused SGD update become ONE graph launch per step, removing ~300 host-side kernel launches.
+
+The training step of the reference (resnet/algos/training.py:94-113) is host-driven op by op; on a
+B200 the WRN-28-10 step is a few milliseconds of GPU time, less than the Python time needed to
+enqueue it, so the launch-bound inner loop is captured once and replayed:
+
+    step = GraphedTrainStep(classifier, optimizer, x_example, y_example)
+    metrics = step(x, y)          # dict of device scalars: loss, top1_err, top5_err
+
+What keeps a replay equal to an eager step:
+  * dropout seeds are folded with a device-side step counter that the graph ticks (fresh masks);
+  * the learning rate lives in a device scalar that FusedSGD refreshes before each replay, so lr
+    schedulers keep working;
+  * BN running statistics / num_batches_tracked are updated by kernels inside the graph;
+  * cached bf16 filter copies are invalidated after every replay (eval after training sees the
+    updated weights).
+Inputs must keep the captured shape; other shapes (e.g. a ragged last batch) run eagerly.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from pytorch_ddp_resnet_b200 import ops
+from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
+from pytorch_ddp_resnet_b200.architectures.layers import invalidate_weight_caches
+
+
+class GraphedTrainStep:
+    def __init__(self, classifier, optimizer, x_example: torch.Tensor, y_example: torch.Tensor,
+                 warmup: Optional[int] = None):
+        if not x_example.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors")
+        self.classifier, self.optimizer = classifier, optimizer
+        self.device = x_example.device
+        self.static_x = torch.empty_like(x_example).copy_(x_example)
+        self.static_y = torch.empty_like(y_example).copy_(y_example)
+        is_ddp = isinstance(classifier, torch.nn.parallel.DistributedDataParallel)
+        warmup = (11 if is_ddp else 3) if warmup is None else warmup  # DDP rebuilds buckets lazily
+        self.eager_steps = 0
+        ops.step_counter(self.device)  # must exist before capture (an in-capture alloc would re-zero it)
+        self.graph = torch.cuda.CUDAGraph()
+        classifier.train()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager(self.static_x, self.static_y)
+                self.eager_steps += 1
+            if hasattr(optimizer, "sync_lr"):
+                optimizer.sync_lr()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        from pytorch_ddp_resnet_b200 import _lib
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            ops.tick(self.device)
+            self.static_metrics = self._eager(self.static_x, self.static_y)
+        self.launches_per_step = _lib.launch_count() - l0  # kernels of ours inside one replay
+        invalidate_weight_caches()
+
+    def _eager(self, x, y) -> Dict[str, torch.Tensor]:
+        m = compute_losses_and_metrics(logits=self.classifier(x), labels=y)
+        m["loss"].backward()
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        return {k: v.detach() for k, v in m.items()}
+
+    def matches(self, x: torch.Tensor, y: torch.Tensor) -> bool:
+        return (x.shape == self.static_x.shape and x.dtype == self.static_x.dtype
+                and y.shape == self.static_y.shape and self.classifier.training)
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One optimisation step. x / y may live on the host (pinned => asynchronous copy)."""
+        if not self.matches(x, y):
+            self.classifier.train()
+            return self._eager(x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True))
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        self.static_x.copy_(x, non_blocking=True)
+        self.static_y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        invalidate_weight_caches()
+        return self.static_metrics

@@ -23,16 +23,27 @@ class FusedSGD(torch.optim.SGD):
         super().__init__(params, **kwargs)
         self._tables = {}   # per device: ring of (pinned host table, device table, event)
         self._ring = 4
+        self._lr_dev = {}   # (group index, device) -> [device fp32 scalar, value it holds]
 
     def _table(self, device, n):
+        """(pinned host table, device table, event) for this step's pointer upload. Eager steps rotate
+        through a small ring (the host may run ahead of the copies); a CUDA-graph capture gets a
+        dedicated pair that no later eager step overwrites, because every replay re-reads it."""
         key = (device, n)
         ring = self._tables.get(key)
         if ring is None:
-            ring = {"slot": 0, "bufs": [
-                (torch.empty((4, n), dtype=torch.int64).pin_memory(),
-                 torch.empty((4, n), dtype=torch.int64, device=device),
-                 torch.cuda.Event()) for _ in range(self._ring)], "used": [False] * self._ring}
+            def pair():
+                return (torch.empty((4, n), dtype=torch.int64).pin_memory(),
+                        torch.empty((4, n), dtype=torch.int64, device=device))
+            ring = {"slot": 0, "bufs": [pair() + (torch.cuda.Event(),) for _ in range(self._ring)],
+                    "used": [False] * self._ring, "capture": [pair() for _ in range(2)], "ncap": 0}
             self._tables[key] = ring
+        if torch.cuda.is_current_stream_capturing():
+            if ring["ncap"] >= len(ring["capture"]):
+                raise RuntimeError("FusedSGD: too many CUDA-graph captures of the same parameter set")
+            host, dev = ring["capture"][ring["ncap"]]
+            ring["ncap"] += 1
+            return host, dev, None
         s = ring["slot"]
         ring["slot"] = (s + 1) % self._ring
         host, dev, ev = ring["bufs"][s]
@@ -40,6 +51,25 @@ class FusedSGD(torch.optim.SGD):
             ev.synchronize()  # the copy issued `ring` steps ago has long finished
         ring["used"][s] = True
         return host, dev, ev
+
+    def _lr_tensor(self, gi, group, device):
+        """Device-resident learning rate of a param group, refreshed whenever the scheduler moved it.
+        The kernel reads it through a pointer, so a captured CUDA graph follows lr schedules."""
+        key = (gi, device)
+        slot = self._lr_dev.get(key)
+        lr = float(group["lr"])
+        if slot is None:
+            slot = [torch.full((), lr, dtype=torch.float32, device=device), lr]
+            self._lr_dev[key] = slot
+        elif slot[1] != lr and not torch.cuda.is_current_stream_capturing():
+            slot[0].fill_(lr)
+            slot[1] = lr
+        return slot[0]
+
+    def sync_lr(self):
+        """Pushes the current param_group lrs to their device scalars (call before a graph replay)."""
+        for (gi, device) in list(self._lr_dev):
+            self._lr_tensor(gi, self.param_groups[gi], device)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -52,7 +82,7 @@ class FusedSGD(torch.optim.SGD):
         inv_scale = None
         if grad_scale is not None:
             inv_scale = grad_scale.double().reciprocal().float()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             if group.get("maximize", False):
                 raise NotImplementedError("FusedSGD: maximize=True is not supported")
             fresh, seasoned = [], []
@@ -84,10 +114,12 @@ class FusedSGD(torch.optim.SGD):
                 host[2] = torch.tensor([b.data_ptr() for _, _, b in items], dtype=torch.int64)
                 host[3] = torch.tensor([p.numel() for p, _, _ in items], dtype=torch.int64)
                 dev.copy_(host, non_blocking=True)
-                ev.record()
+                if ev is not None:
+                    ev.record()
                 ops.sgd_step(dev, n, max(p.numel() for p, _, _ in items), group["lr"], group["momentum"],
                              group["dampening"], group["weight_decay"], group["nesterov"], first,
-                             inv_scale=inv_scale, found_inf=found_inf)
+                             inv_scale=inv_scale, found_inf=found_inf,
+                             lr_dev=self._lr_tensor(gi, group, device))
                 for p, _, _ in items:
                     torch.autograd.graph.increment_version(p)
                 self._keepalive = items  # grads copied above must outlive the launch

@@ -223,6 +223,53 @@ def test_loss_curve_matches_bf16_oracle_200_steps():
     assert (mine_t - ref_t).abs().max() < 0.1
 
 
+def test_cuda_graph_step_equals_eager_steps():
+    """The captured whole-step graph must produce the same parameters as eager stepping (p = 0), and
+    fresh dropout masks at every replay (p > 0)."""
+    from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
+    from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
+    spec = "c3,16,3,1,1 r1 r1 n a ap16,1,0 fc32,10"
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(8, 3, 32, 32, generator=g).cuda() for _ in range(6)]
+    ys = [torch.randint(0, 10, (8,), generator=g).cuda() for _ in range(6)]
+    torch.manual_seed(0)
+    m1 = ResNet(spec, True, True, 0.0).cuda().train()
+    m2 = ResNet(spec, True, True, 0.0).cuda().train()
+    m2.load_state_dict(m1.state_dict())
+    o1 = get_optimizer("SGD", m1, dict(SGD))
+    o2 = get_optimizer("SGD", m2, dict(SGD))
+    sched = torch.optim.lr_scheduler.MultiStepLR(o2, milestones=[5], gamma=0.1)
+    sched1 = torch.optim.lr_scheduler.MultiStepLR(o1, milestones=[5], gamma=0.1)
+    warm = 3
+    step = GraphedTrainStep(m2, o2, xs[0], ys[0], warmup=warm)  # 3 eager steps on xs[0] inside
+    for _ in range(warm):
+        sched.step()
+    losses2 = []
+    for i in range(6):
+        losses2.append(step(xs[i], ys[i])["loss"].item())
+        sched.step()
+    losses1 = []
+    for i in [0] * warm + list(range(6)):
+        l = compute_losses_and_metrics(logits=m1(xs[i]), labels=ys[i])["loss"]
+        l.backward(); o1.step(); o1.zero_grad(set_to_none=True); sched1.step()
+        losses1.append(l.item())
+    assert losses1[warm:] == pytest.approx(losses2, rel=1e-5, abs=1e-6)
+    for (n1, p1), (_, p2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.allclose(p1.float(), p2.float(), atol=1e-6, rtol=1e-5), n1
+    # eval after graph replays must see the updated weights (bf16 filter caches are invalidated)
+    m1.eval(); m2.eval()
+    with torch.no_grad():
+        assert torch.equal(m1(xs[0]), m2(xs[0]))
+    # dropout: every replay draws a new mask
+    m3 = ResNet(spec, True, True, 0.3).cuda().train()
+    o3 = get_optimizer("SGD", m3, dict(lr=0.0, momentum=0.0))
+    step3 = GraphedTrainStep(m3, o3, xs[0], ys[0])
+    ls = [step3(xs[0], ys[0])["loss"].item() for _ in range(4)]
+    assert len(set(ls)) == 4, ls
+
+
 def test_no_silent_fallback_when_library_missing(monkeypatch):
     from pytorch_ddp_resnet_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
