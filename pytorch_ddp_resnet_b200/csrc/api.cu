@@ -687,15 +687,16 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
   a.seed_offset = seed_offset;
-  const size_t smem = (size_t)2 * C * sizeof(float);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(bn_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   200 * 1024));
-    attr_set = true;
+  {
+    const int CG = C / 8;
+    const int CGb = std::min(EW_THREADS, CG);
+    const int RP = EW_THREADS / CGb;
+    const int64_t rows = (int64_t)N * H * W;
+    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 4 - 1) / ((int64_t)RP * 4),
+                                                          (int64_t)num_sms() * 8));
+    dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
+    bn_act_fwd_kernel<<<grid, EW_THREADS, 0, as_stream(stream)>>>(a);
   }
-  const size_t nvec = (size_t)N * H * W * C / 8;
-  bn_act_fwd_kernel<<<ew_grid(nvec), EW_THREADS, smem, as_stream(stream)>>>(a);
   B200_LAUNCH_CHECK("bn_act_fwd_kernel");
   return 0;
 }
@@ -730,15 +731,15 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
     bn_bwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
     B200_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   }
-  const size_t smem = a.affine ? (size_t)5 * C * sizeof(float) : 0;
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(bn_act_bwd_apply_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  {
+    const int CG = C / 8;
+    const int CGb = std::min(EW_THREADS, CG);
+    const int RP = EW_THREADS / CGb;
+    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 2 - 1) / ((int64_t)RP * 2),
+                                                          (int64_t)num_sms() * 8));
+    dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
+    bn_act_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>(a);
   }
-  const size_t nvec = (size_t)rows * C / 8;
-  bn_act_bwd_apply_kernel<<<ew_grid(nvec), EW_THREADS, smem, st>>>(a);
   B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;
 }

@@ -24,6 +24,19 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a fully converged warp (the same lane every time): the issuer of TMA / tcgen05 ops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,6 +245,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
+}
+
+// The descriptor split in two 32-bit halves: the high word is constant for a kernel, the low word is
+// (start address >> 4) | (LBO >> 4) << 16 and advances by plain integer adds.
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3ffffu) >> 4) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
 
 // 32-bit instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.

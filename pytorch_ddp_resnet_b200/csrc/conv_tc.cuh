@@ -100,66 +100,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_hw = args.tiles_w * args.tiles_h;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-        const int nt = tile % args.n_ntiles;
-        const int mt = tile / args.n_ntiles;
-        const int w0 = (mt % args.tiles_w) * args.bw;
-        const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
-        const int n0 = (mt / tiles_hw) * args.bn;
-        for (int t = 0; t < args.taps.n; ++t) {
-          const int cw = w0 + args.taps.dw[t];
-          const int ch = h0 + args.taps.dh[t];
-          const int cn = n0 + args.taps.dn[t];
-          const int wc = args.taps.wcol[t];
-          for (int kc = 0; kc < args.nkc; ++kc) {
-            mbar_wait(&empty_bar[s], ph ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) ==============
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const int nt = tile % args.n_ntiles;
+      const int mt = tile / args.n_ntiles;
+      const int w0 = (mt % args.tiles_w) * args.bw;
+      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
+      const int n0 = (mt / tiles_hw) * args.bn;
+      for (int t = 0; t < args.taps.n; ++t) {
+        const int cw = w0 + args.taps.dw[t];
+        const int ch = h0 + args.taps.dh[t];
+        const int cn = n0 + args.taps.dn[t];
+        const int wc = args.taps.wcol[t];
+        for (int kc = 0; kc < args.nkc; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
             uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
             uint8_t* b_dst = a_dst + args.a_bytes;
             mbar_expect_tx(&full_bar[s], args.tx_bytes);
             tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw, ch, cn);
             tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
-            if (++s == args.stages) { s = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++s == args.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = make_idesc_bf16(128, args.BN, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      const int nk = args.taps.n * args.nkc;
-      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aph ^ 1);
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) ================
+    const uint32_t idesc = make_idesc_bf16(128, args.BN, 0, 0);
+    const uint32_t dhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
+    const uint32_t smem_base = smem_u32(smem);
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    const int nk = args.taps.n * args.nkc;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
+      for (int it = 0; it < nk; ++it) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
-        for (int it = 0; it < nk; ++it) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * args.stage_bytes);
-          const uint32_t b_addr = a_addr + args.a_bytes;
+        if (elect_one()) {
+          const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
+          const uint32_t alo = smem_desc_lo(a_addr, 16);
+          const uint32_t blo = smem_desc_lo(a_addr + args.a_bytes, 16);
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, KMajorCfg<KC>::SBO,
-                                               KMajorCfg<KC>::LAYOUT);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, KMajorCfg<KC>::SBO,
-                                               KMajorCfg<KC>::LAYOUT);
-            umma_bf16_ss(d_addr, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(d_addr, smem_desc_join(alo + 2 * k, dhi), smem_desc_join(blo + 2 * k, dhi),
+                         idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
-          if (++s == args.stages) { s = 0; ph ^= 1; }
+          if (it == nk - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&tfull_bar[as]);
-        as ^= 1;
-        if (as == 0) aph ^= 1;
+        __syncwarp();
+        if (++s == args.stages) { s = 0; ph ^= 1; }
       }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
     }
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
@@ -311,15 +313,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t b_off = Cfg::SLABS_PER_MTILE * args.slab_bytes;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t tx = (uint32_t)(na + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        const int w0 = (pt % args.tiles_w) * args.bw;
-        const int h0 = ((pt / args.tiles_w) % args.tiles_h) * args.bh;
-        const int n0 = (pt / tiles_hw) * args.bn;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t tx = (uint32_t)(na + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      const int w0 = (pt % args.tiles_w) * args.bw;
+      const int h0 = ((pt / args.tiles_w) % args.tiles_h) * args.bh;
+      const int n0 = (pt / tiles_hw) * args.bn;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
         uint8_t* b_dst = a_dst + b_off;
         mbar_expect_tx(&full_bar[s], tx);
@@ -334,31 +336,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
                       nt * args.BN + i * SL, w0, h0, n0);
         }
-        if (++s == args.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == args.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, args.BN, 1, 1);
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t first = 1;
-      for (int pt = pt0; pt < pt1; ++pt) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * args.stage_bytes);
-        const uint32_t b_addr = a_addr + b_off;
+    const uint32_t idesc = make_idesc_bf16(128, args.BN, 1, 1);
+    const uint32_t dhi = smem_desc_hi(Cfg::SBO, Cfg::LAYOUT);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t kstep = (16u * Cfg::ROW_BYTES) >> 4;  // descriptor-address units per 16 pixels
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
+        const uint32_t alo = smem_desc_lo(a_addr, Cfg::LBO);
+        const uint32_t blo = smem_desc_lo(a_addr + b_off, Cfg::LBO);
         for (int k = 0; k < args.kmmas; ++k) {
-          const uint32_t koff = (uint32_t)k * 16u * Cfg::ROW_BYTES;
-          const uint64_t ad = make_smem_desc(a_addr + koff, Cfg::LBO, Cfg::SBO, Cfg::LAYOUT);
-          const uint64_t bd = make_smem_desc(b_addr + koff, Cfg::LBO, Cfg::SBO, Cfg::LAYOUT);
-          umma_bf16_ss(tmem_base, ad, bd, idesc, first ? 0u : 1u);
-          first = 0;
+          umma_bf16_ss(tmem_base, smem_desc_join(alo + k * kstep, dhi),
+                       smem_desc_join(blo + k * kstep, dhi), idesc, (pt > pt0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
-        if (++s == args.stages) { s = 0; ph ^= 1; }
+        if (pt == pt1 - 1) umma_commit(&tfull_bar);
       }
-      umma_commit(&tfull_bar);
+      __syncwarp();
+      if (++s == args.stages) { s = 0; ph ^= 1; }
+    }
+    if (pt1 <= pt0) {
+      if (elect_one()) umma_commit(&tfull_bar);
+      __syncwarp();
     }
   } else if (pt1 > pt0) {
     // epilogue: lane m of the accumulator is (slab, channel) = (m / SL, m % SL)

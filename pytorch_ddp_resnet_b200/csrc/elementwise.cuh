@@ -69,7 +69,23 @@ bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(rows, r0 + rows_per_block);
     const bf16* base = x + (size_t)(g.cg0 + g.cgl) * 8;
-    for (int64_t r = r0 + g.rl; r < r1; r += g.RP) {
+    int64_t r = r0 + g.rl;
+    for (; r + 3 * (int64_t)g.RP < r1; r += 4 * (int64_t)g.RP) {
+      Vec8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].raw = ldg_stream(base + (size_t)(r + u * (int64_t)g.RP) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        v[u].to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += f[j];
+          acc[8 + j] = fmaf(f[j], f[j], acc[8 + j]);
+        }
+      }
+    }
+    for (; r < r1; r += g.RP) {
       Vec8 v;
       v.raw = ldg_stream(base + (size_t)r * C);
       float f[8];
@@ -152,70 +168,83 @@ struct BnActFwdArgs {
   const uint64_t* seed_offset;  // device step counter folded into the seed (CUDA-graph replays)
 };
 
+// Thread mapping of the element-wise BN kernels: a thread owns ONE 8-channel group for the whole
+// kernel (per-channel coefficients live in registers) and walks rows with stride RP * gridDim.x;
+// the RP x CGb threads of a block touch RP consecutive rows = one contiguous 4 KB span per pass.
 __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdArgs a) {
-  extern __shared__ float ab_smem[];  // [2][C]: scale, shift
   const int C = a.C;
+  ReduceGeom g(C);
+  if (!g.active) return;
+  const int cgi = g.cg0 + g.cgl;
+  float sc[8], sh[8];
   if (a.affine) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cgi * 8 + j;
       const float is = a.stat_is_var ? rsqrtf(a.invstd[c] + a.eps) : a.invstd[c];
-      const float sc = a.gamma[c] * is;
-      ab_smem[c] = sc;
-      ab_smem[C + c] = a.beta[c] - a.mean[c] * sc;
+      sc[j] = a.gamma[c] * is;
+      sh[j] = a.beta[c] - a.mean[c] * sc[j];
     }
-    __syncthreads();
   }
-  const int CG = C / 8;
-  const size_t nvec = (size_t)a.N * a.H * a.W * CG;
+  const int64_t rows = (int64_t)a.N * a.H * a.W;
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-       v += (size_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(v % CG);
-    Vec8 xv;
-    xv.raw = ldg_stream(a.x + v * 8);
-    float f[8];
-    xv.to_float(f);
-    if (a.affine) {
+  const bool skip_here = a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C);
+  const int64_t stride = (int64_t)g.RP * gridDim.x;
+  constexpr int U = 4;
+  for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < rows; r0 += U * stride) {
+    Vec8 xv[U], sv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        f[j] = round_bf16(fmaf(f[j], ab_smem[cg * 8 + j], ab_smem[C + cg * 8 + j]));
-    }
-    if (a.skip_mode == 1) {
-      Vec8 sv;
-      sv.raw = ldg_stream(a.skip + v * 8);
-      float s[8];
-      sv.to_float(s);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + s[j]);
-    } else if (a.skip_mode == 2) {
-      if (cg * 8 < a.skip_C) {
-        const size_t pix = v / CG;
-        const int w = (int)(pix % a.W);
-        const int h = (int)((pix / a.W) % a.H);
-        const int n = (int)(pix / ((size_t)a.W * a.H));
-        const size_t spix = ((size_t)n * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w;
-        Vec8 sv;
-        sv.raw = ldg_stream(a.skip + spix * a.skip_C + (size_t)cg * 8);
-        float s[8];
-        sv.to_float(s);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + s[j]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) {
+        xv[u].raw = ldg_stream(a.x + ((size_t)r * g.CG + cgi) * 8);
+        if (skip_here) {
+          size_t so;
+          if (a.skip_mode == 1) {
+            so = ((size_t)r * g.CG + cgi) * 8;
+          } else {
+            const int w = (int)(r % a.W);
+            const int h = (int)((r / a.W) % a.H);
+            const int n = (int)(r / ((int64_t)a.W * a.H));
+            so = (((size_t)n * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w) * a.skip_C + (size_t)cgi * 8;
+          }
+          sv[u].raw = ldg_stream(a.skip + so);
+        }
       }
     }
-    if (a.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    if (a.drop_thr) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= rows) break;
+      const size_t v = (size_t)r * g.CG + cgi;
+      float f[8];
+      xv[u].to_float(f);
+      if (a.affine) {
 #pragma unroll
-      for (int j2 = 0; j2 < 4; ++j2) {
-        const uint32_t d = rng_draw(seed, v * 4 + j2);
-        f[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2] * a.inv_keep);
-        f[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2 + 1] * a.inv_keep);
+        for (int j = 0; j < 8; ++j) f[j] = round_bf16(fmaf(f[j], sc[j], sh[j]));
       }
+      if (skip_here) {
+        float sk[8];
+        sv[u].to_float(sk);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + sk[j]);
+      }
+      if (a.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (a.drop_thr) {
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const uint32_t d = rng_draw(seed, v * 4 + j2);
+          f[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2] * a.inv_keep);
+          f[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2 + 1] * a.inv_keep);
+        }
+      }
+      Vec8 o;
+      o.from_float(f);
+      stg_stream(a.y + v * 8, o.raw);
     }
-    Vec8 o;
-    o.from_float(f);
-    stg_stream(a.y + v * 8, o.raw);
   }
 }
 
@@ -244,9 +273,8 @@ struct BnActBwdArgs {
 };
 
 // g = dy masked by relu (y != 0) and dropout (regenerated from the counter RNG), scaled by 1/(1-p)
-__device__ __forceinline__ void masked_grad(const BnActBwdArgs& a, uint64_t seed, size_t v, float* g) {
-  Vec8 dv;
-  dv.raw = ldg_stream(a.dy + v * 8);
+__device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t seed, size_t v,
+                                                 const Vec8& dv, const Vec8& yv, float* g) {
   dv.to_float(g);
   if (a.drop_thr) {
 #pragma unroll
@@ -257,8 +285,6 @@ __device__ __forceinline__ void masked_grad(const BnActBwdArgs& a, uint64_t seed
     }
   }
   if (a.relu) {
-    Vec8 yv;
-    yv.raw = ldg_stream(a.y + v * 8);
     float yf[8];
     yv.to_float(yf);
 #pragma unroll
@@ -286,18 +312,32 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
     const int64_t rows_per_block = (a.rows + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(a.rows, r0 + rows_per_block);
-    for (int64_t r = r0 + g.rl; r < r1; r += g.RP) {
-      const size_t v = (size_t)r * g.CG + cgi;
-      float gr[8];
-      masked_grad(a, seed, v, gr);
-      Vec8 xv;
-      xv.raw = ldg_stream(a.x + v * 8);
-      float xf[8];
-      xv.to_float(xf);
+    constexpr int U = 2;
+    for (int64_t rb = r0 + g.rl; rb < r1; rb += U * (int64_t)g.RP) {
+      Vec8 dv[U], yv[U], xv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] += gr[j];
-        acc[8 + j] = fmaf(gr[j], (xf[j] - mu[j]) * is[j], acc[8 + j]);
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = rb + u * (int64_t)g.RP;
+        if (r < r1) {
+          const size_t v = (size_t)r * g.CG + cgi;
+          dv[u].raw = ldg_stream(a.dy + v * 8);
+          if (a.relu) yv[u].raw = ldg_stream(a.y + v * 8);
+          xv[u].raw = ldg_stream(a.x + v * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = rb + u * (int64_t)g.RP;
+        if (r >= r1) break;
+        const size_t v = (size_t)r * g.CG + cgi;
+        float gr[8], xf[8];
+        masked_grad_from(a, seed, v, dv[u], yv[u], gr);
+        xv[u].to_float(xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += gr[j];
+          acc[8 + j] = fmaf(gr[j], (xf[j] - mu[j]) * is[j], acc[8 + j]);
+        }
       }
     }
   }
@@ -315,62 +355,73 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float
   dgamma[c] = (float)sx;
 }
 
-// dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g
+// dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g.
+// Per channel this is dx = k1 * g + k2 * x + k3 with
+//   k1 = gamma*invstd, k2 = -k1*invstd*dgamma/rows, k3 = -k1*dbeta/rows - k2*mean   (registers).
 __global__ void __launch_bounds__(EW_THREADS) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
-  extern __shared__ float ch_smem[];  // [4][C]: mean, invstd, gamma*invstd, then dgamma/dbeta scaled
   const int C = a.C;
+  ReduceGeom g(C);
+  if (!g.active) return;
+  const int cgi = g.cg0 + g.cgl;
+  float k1[8], k2[8], k3[8];
   if (a.affine) {
     const float inv_rows = 1.f / (float)a.rows;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      ch_smem[c] = a.mean[c];
-      ch_smem[C + c] = a.invstd[c];
-      ch_smem[2 * C + c] = a.gamma[c] * a.invstd[c];
-      ch_smem[3 * C + c] = a.dbeta[c] * inv_rows;
-      ch_smem[4 * C + c] = a.dgamma[c] * inv_rows;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cgi * 8 + j;
+      const float is = a.invstd[c];
+      k1[j] = a.gamma[c] * is;
+      k2[j] = -k1[j] * is * a.dgamma[c] * inv_rows;
+      k3[j] = -k1[j] * a.dbeta[c] * inv_rows - k2[j] * a.mean[c];
     }
-    __syncthreads();
   }
-  const int CG = C / 8;
-  const size_t nvec = (size_t)a.rows * CG;
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-       v += (size_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(v % CG);
-    float g[8];
-    masked_grad(a, seed, v, g);
-    if (a.dskip) {
-      Vec8 o;
-      o.from_float(g);
-      stg_stream(a.dskip + v * 8, o.raw);
-    }
-    float d[8];
-    if (a.affine) {
-      Vec8 xv;
-      xv.raw = ldg_stream(a.x + v * 8);
-      float xf[8];
-      xv.to_float(xf);
+  const int64_t stride = (int64_t)g.RP * gridDim.x;
+  constexpr int U = 2;
+  for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < a.rows; r0 += U * stride) {
+    Vec8 dv[U], yv[U], xv[U], av[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float xhat = (xf[j] - ch_smem[c]) * ch_smem[C + c];
-        d[j] = round_bf16(ch_smem[2 * C + c] *
-                          (g[j] - ch_smem[3 * C + c] - xhat * ch_smem[4 * C + c]));
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < a.rows) {
+        const size_t v = (size_t)r * g.CG + cgi;
+        dv[u].raw = ldg_stream(a.dy + v * 8);
+        if (a.relu) yv[u].raw = ldg_stream(a.y + v * 8);
+        if (a.affine) xv[u].raw = ldg_stream(a.x + v * 8);
+        if (a.addend) av[u].raw = ldg_stream(a.addend + v * 8);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = g[j];
     }
-    if (a.addend) {
-      Vec8 av;
-      av.raw = ldg_stream(a.addend + v * 8);
-      float af[8];
-      av.to_float(af);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = round_bf16(d[j] + af[j]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= a.rows) break;
+      const size_t v = (size_t)r * g.CG + cgi;
+      float gr[8], d[8];
+      masked_grad_from(a, seed, v, dv[u], yv[u], gr);
+      if (a.dskip) {
+        Vec8 o;
+        o.from_float(gr);
+        stg_stream(a.dskip + v * 8, o.raw);
+      }
+      if (a.affine) {
+        float xf[8];
+        xv[u].to_float(xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = round_bf16(fmaf(k1[j], gr[j], fmaf(k2[j], xf[j], k3[j])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = gr[j];
+      }
+      if (a.addend) {
+        float af[8];
+        av[u].to_float(af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = round_bf16(d[j] + af[j]);
+      }
+      Vec8 o;
+      o.from_float(d);
+      stg_stream(a.dx + v * 8, o.raw);
     }
-    Vec8 o;
-    o.from_float(d);
-    stg_stream(a.dx + v * 8, o.raw);
   }
 }
 

@@ -1,0 +1,81 @@
+"""
+Multi-GPU (NCCL) checks of the data-parallel path; skipped unless the box has >= 2 GPUs
+(run with `gpurun --gpus 2 -- python -m pytest tests/test_ddp_gpu.py -m gpu`).
+DDP over our autograd Functions must give every rank the mean of the per-rank gradients, keep the
+replicas identical after FusedSGD steps, and keep BatchNorm statistics per-rank local (rank 0's
+running stats are broadcast to the others before each forward, like the reference's default DDP).
+"""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = pytest.mark.gpu
+SPEC = "c3,32,3,1,1 r1 r1 n a ap16,1,0 fc64,10"
+SGD = dict(lr=0.1, momentum=0.9, dampening=0.0, nesterov=True, weight_decay=5e-4)
+
+
+def _worker(rank, world, port, use_graph):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
+    from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
+
+    torch.manual_seed(0)  # identical initial replicas
+    model = ResNet(SPEC, True, True, 0.0).cuda()
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank])
+    g = torch.Generator().manual_seed(100 + rank)  # different data per rank
+    x = torch.randn(8, 3, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 10, (8,), generator=g).cuda()
+
+    # (1) DDP gradient == mean over ranks of the local gradients
+    ddp.train()
+    compute_losses_and_metrics(logits=ddp(x), labels=y)["loss"].backward()
+    ddp_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    local = ResNet(SPEC, True, True, 0.0).cuda().train()
+    local.load_state_dict(init)
+    compute_losses_and_metrics(logits=local(x), labels=y)["loss"].backward()
+    for n, p in local.named_parameters():
+        gmean = p.grad.clone()
+        dist.all_reduce(gmean)
+        gmean /= world
+        err = ((ddp_grads[n] - gmean).norm() / gmean.norm().clamp_min(1e-12)).item()
+        assert err < 1e-3, (n, err)
+
+    # (2) replicas stay identical through optimizer steps (eager or whole-step CUDA graph)
+    opt = get_optimizer("SGD", ddp, dict(SGD))
+    opt.zero_grad(set_to_none=True)
+    if use_graph:
+        step = GraphedTrainStep(ddp, opt, x, y)
+        for _ in range(3):
+            step(x, y)
+    else:
+        for _ in range(3):
+            compute_losses_and_metrics(logits=ddp(x), labels=y)["loss"].backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    for n, p in model.named_parameters():
+        ref = p.detach().clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, p.detach()), f"replicas diverged at {n}"
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_ddp_two_ranks(use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = 29500 + os.getpid() % 1000 + (7 if use_graph else 0)
+    mp.spawn(_worker, args=(2, port, use_graph), nprocs=2, join=True)
