@@ -195,16 +195,17 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        from pytorch_ddp_resnet_b200.utils.ddp_util import prepare_env_for_graphs, wrap_ddp
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        prepare_env_for_graphs()
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     _lib.load()
 
     torch.manual_seed(0)
     model = ResNet(SPEC, PREACT, USE_PROJ, DROPOUT).to(device).train()
     if world > 1:
-        classifier = torch.nn.parallel.DistributedDataParallel(
-            model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        classifier = wrap_ddp(model, device)
     else:
         classifier = model
     opt = get_optimizer("SGD", classifier, dict(SGD))

@@ -128,7 +128,11 @@ class Conv2d(tc.nn.Module):
 
 
 def conv_weight_grad(dw_krsc: torch.Tensor) -> torch.Tensor:
-    """fp32 [K,R,S,C] kernel output -> gradient shaped like the [O,I,kh,kw] channels_last parameter."""
+    """fp32 [K,R,S,C] kernel output -> gradient shaped like the [O,I,kh,kw] channels_last parameter
+    (same strides as the parameter, so autograd / DDP bucket views take it without a copy)."""
+    K, R, S, C = dw_krsc.shape
+    if R == 1 and S == 1:
+        return dw_krsc.view(K, C, 1, 1)
     return dw_krsc.permute(0, 3, 1, 2)
 
 

@@ -17,6 +17,12 @@ What keeps a replay equal to an eager step:
   * cached bf16 filter copies are invalidated after every replay (eval after training sees the
     updated weights).
 Inputs must keep the captured shape; other shapes (e.g. a ragged last batch) run eagerly.
+
+Data parallel (classifier is a DistributedDataParallel wrapper): the graph holds forward + backward of
+the LOCAL module (no DDP hooks run inside a capture); each replay is followed by ONE coalesced NCCL
+all-reduce (average) over the static gradient buffers and the fused SGD launch. BatchNorm buffers stay
+per-rank during graphed training and are re-synchronised from rank 0 whenever the DDP wrapper runs a
+forward (evaluation, eager steps), which is where the reference's per-forward broadcast is observable.
 """
 from typing import Dict, Optional
 
@@ -36,8 +42,10 @@ class GraphedTrainStep:
         self.device = x_example.device
         self.static_x = torch.empty_like(x_example).copy_(x_example)
         self.static_y = torch.empty_like(y_example).copy_(y_example)
-        is_ddp = isinstance(classifier, torch.nn.parallel.DistributedDataParallel)
-        warmup = (11 if is_ddp else 3) if warmup is None else warmup  # DDP rebuilds buckets lazily
+        self.is_ddp = isinstance(classifier, torch.nn.parallel.DistributedDataParallel)
+        self.local = classifier.module if self.is_ddp else classifier
+        self.world = torch.distributed.get_world_size() if self.is_ddp else 1
+        warmup = 3 if warmup is None else warmup
         self.eager_steps = 0
         ops.step_counter(self.device)  # must exist before capture (an in-capture alloc would re-zero it)
         self.graph = torch.cuda.CUDAGraph()
@@ -56,16 +64,44 @@ class GraphedTrainStep:
         l0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             ops.tick(self.device)
-            self.static_metrics = self._eager(self.static_x, self.static_y)
+            self.static_metrics = self._forward_backward(self.local, self.static_x, self.static_y)
+            if not self.is_ddp:
+                self.optimizer.step()
+                self.optimizer.zero_grad(set_to_none=True)
         self.launches_per_step = _lib.launch_count() - l0  # kernels of ours inside one replay
+        if self.is_ddp:
+            # .grad now aliases the graph's static gradient buffers; every replay rewrites them
+            self.grad_owners = [p for p in self.local.parameters() if p.grad is not None]
+            self.grads = [p.grad for p in self.grad_owners]
+            self.launches_per_step += 1  # the SGD launch that follows each replay
+            self._reduce_and_step()      # finish the step that the capture pass computed
         invalidate_weight_caches()
 
-    def _eager(self, x, y) -> Dict[str, torch.Tensor]:
-        m = compute_losses_and_metrics(logits=self.classifier(x), labels=y)
+    @staticmethod
+    def _forward_backward(module, x, y) -> Dict[str, torch.Tensor]:
+        m = compute_losses_and_metrics(logits=module(x), labels=y)
         m["loss"].backward()
+        return {k: v.detach() for k, v in m.items()}
+
+    def _allreduce(self, grads) -> None:
+        """Gradient averaging over ranks: one coalesced NCCL launch over all gradient tensors."""
+        dist = torch.distributed
+        with dist._coalescing_manager(device=self.device, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+
+    def _reduce_and_step(self) -> None:
+        self._allreduce(self.grads)
+        self.optimizer.step()
+
+    def _eager(self, x, y) -> Dict[str, torch.Tensor]:
+        """One un-captured optimisation step with the same maths as a replay."""
+        m = self._forward_backward(self.local, x, y)
+        if self.is_ddp:
+            self._allreduce([p.grad for p in self.local.parameters() if p.grad is not None])
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
-        return {k: v.detach() for k, v in m.items()}
+        return m
 
     def matches(self, x: torch.Tensor, y: torch.Tensor) -> bool:
         return (x.shape == self.static_x.shape and x.dtype == self.static_x.dtype
@@ -75,11 +111,19 @@ class GraphedTrainStep:
         """One optimisation step. x / y may live on the host (pinned => asynchronous copy)."""
         if not self.matches(x, y):
             self.classifier.train()
-            return self._eager(x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True))
+            if self.is_ddp:  # detach the static gradient buffers for the duration of the eager step
+                self.optimizer.zero_grad(set_to_none=True)
+            out = self._eager(x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True))
+            if self.is_ddp:
+                for p, g in zip(self.grad_owners, self.grads):
+                    p.grad = g
+            return out
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()
+        if self.is_ddp:
+            self._reduce_and_step()
         invalidate_weight_caches()
         return self.static_metrics

@@ -24,6 +24,8 @@ def _worker(rank, world, port, use_graph):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
+    from pytorch_ddp_resnet_b200.utils.ddp_util import prepare_env_for_graphs, wrap_ddp
+    prepare_env_for_graphs()
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
     from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
@@ -33,7 +35,7 @@ def _worker(rank, world, port, use_graph):
     torch.manual_seed(0)  # identical initial replicas
     model = ResNet(SPEC, True, True, 0.0).cuda()
     init = {k: v.clone() for k, v in model.state_dict().items()}
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank])
+    ddp = wrap_ddp(model, torch.device("cuda", rank))
     g = torch.Generator().manual_seed(100 + rank)  # different data per rank
     x = torch.randn(8, 3, 32, 32, generator=g).cuda()
     y = torch.randint(0, 10, (8,), generator=g).cuda()
