@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -249,13 +250,24 @@ static bool use_tc(int algo, int pass, int N, int H, int W, int C, int K, int R,
   return b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad) != 0;
 }
 
-template <int KC>
+static int conv_cluster_size() {
+  // B200_CONV_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing one multicast filter tile
+  static int cs = 0;
+  if (cs == 0) {
+    const char* e = getenv("B200_CONV_CLUSTER");
+    cs = e ? atoi(e) : 2;
+    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  }
+  return cs;
+}
+
+template <int KC, int CS>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                           cudaStream_t st) {
   static bool attr_set = false;
   const int max_dyn = 228352;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    max_dyn));
     attr_set = true;
   }
@@ -267,10 +279,90 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
   a.tx_bytes = (uint32_t)a.rows_valid * KC * 2u + (uint32_t)a.BN * KC * 2u;
   size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
   dyn = std::max<size_t>(dyn, 120 * 1024);  // one CTA per SM: the CTA owns all 512 TMEM columns
-  const int grid = std::min(a.num_tiles, num_sms());
-  conv_tc_kernel<KC><<<grid, TC_THREADS, dyn, st>>>(tmA, tmB, a);
+  const int num_ctiles = a.num_tiles / CS;
+  const int grid = std::min(num_ctiles, num_sms() / CS) * CS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, CS>, tmA, tmB, a));
   B200_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
+}
+
+// SM-pair (cta_group::2) launch: tmB's box holds BN/2 filter rows
+template <int KC>
+static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
+                           cudaStream_t st) {
+  static bool attr_set = false;
+  const int max_dyn = 228352;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_dyn));
+    attr_set = true;
+  }
+  a.a_bytes = 128u * KC * 2u;
+  const uint32_t b_bytes = ((uint32_t)(a.BN / 2) * KC * 2u + 1023u) & ~1023u;
+  a.block_bytes = a.a_bytes + b_bytes;
+  a.tx_bytes = (uint32_t)a.rows_valid * KC * 2u + (uint32_t)(a.BN / 2) * KC * 2u;  // per CTA, per block
+  // K-blocks per stage: at least 8 MMAs per barrier round trip (the issue loop costs ~500 cycles per
+  // iteration), as long as three stages still fit
+  const int budget = max_dyn - 1024;
+  int gblk = std::max(1, 8 / (KC / 16));
+  if (const char* e = getenv("B200_CONV_GBLK")) gblk = std::max(1, atoi(e));
+  gblk = std::min(gblk, a.taps.n * a.nkc);
+  while (gblk > 1 && budget / (int)(gblk * a.block_bytes) < 3) --gblk;
+  a.gblk = gblk;
+  a.stage_bytes = (uint32_t)gblk * a.block_bytes;
+  a.stages = std::min<int>(TC_MAX_STAGES, budget / (int)a.stage_bytes);
+  B200_REQUIRE(a.stages >= 2, "conv_tc2: tile does not fit in shared memory");
+  size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
+  dyn = std::max<size_t>(dyn, 120 * 1024);
+  const int num_ptiles = a.num_tiles / 2;
+  const int grid = std::min(num_ptiles, num_sms() / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<KC>, tmA, tmB, a));
+  B200_LAUNCH_CHECK("conv_tc2_kernel");
+  return 0;
+}
+
+static bool conv_use_pair() {
+  // B200_CONV_PAIR=0 disables the cta_group::2 kernel (falls back to the single-CTA kernel)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_CONV_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+template <int KC>
+static int launch_conv_tc_cs(int cs, const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
+                             cudaStream_t st) {
+  switch (cs) {
+    case 4: return launch_conv_tc<KC, 4>(tmA, tmB, a, st);
+    case 2: return launch_conv_tc<KC, 2>(tmA, tmB, a, st);
+    default: return launch_conv_tc<KC, 1>(tmA, tmB, a, st);
+  }
 }
 
 // One shifted-window GEMM launch. act: [Nact][Ha][Wa][Cin] (bf16), wmat: [Cout][ntaps*Cin] (bf16),
@@ -293,13 +385,30 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
+  const int m_tiles_all = t.tiles_w * t.tiles_h * t.tiles_n;
+  if (conv_use_pair() && m_tiles_all % 2 == 0 && BN % 32 == 0) {
+    // SM pair: every CTA stages BN/2 filter rows (whole 8-row swizzle atoms, UMMA N multiple of 16)
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
+    if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
+    switch (KC) {
+      case 64: return launch_conv_tc2<64>(tmA, tmB, a, st);
+      case 32: return launch_conv_tc2<32>(tmA, tmB, a, st);
+      default: return launch_conv_tc2<16>(tmA, tmB, a, st);
+    }
+  }
+  // cluster size: the pixel-tile count must split evenly and every filter slice must be whole 8-row
+  // swizzle atoms
+  int cs = conv_cluster_size();
+  const int m_tiles = t.tiles_w * t.tiles_h * t.tiles_n;
+  while (cs > 1 && (m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0)) cs /= 2;
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
-  if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN)) return rc;
+  if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / cs)) return rc;
   switch (KC) {
-    case 64: return launch_conv_tc<64>(tmA, tmB, a, st);
-    case 32: return launch_conv_tc<32>(tmA, tmB, a, st);
-    default: return launch_conv_tc<16>(tmA, tmB, a, st);
+    case 64: return launch_conv_tc_cs<64>(cs, tmA, tmB, a, st);
+    case 32: return launch_conv_tc_cs<32>(cs, tmA, tmB, a, st);
+    default: return launch_conv_tc_cs<16>(cs, tmA, tmB, a, st);
   }
 }
 

@@ -21,7 +21,7 @@
 namespace b200 {
 
 constexpr int TC_MAX_TAPS = 9;
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 20;
 constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 
 struct TapTable {
@@ -45,7 +45,9 @@ struct ConvTcArgs {
   int stages;
   uint32_t stage_bytes;
   uint32_t a_bytes;                 // 128 * KC * 2
-  uint32_t tx_bytes;                // bytes landed per stage
+  uint32_t tx_bytes;                // bytes landed per K-block (per CTA)
+  int gblk;                         // K-blocks per pipeline stage (SM-pair kernel)
+  uint32_t block_bytes;             // shared-memory bytes of one K-block (A tile + B tile)
   TapTable taps;
   bf16* out;
   const bf16* residual;
@@ -59,7 +61,10 @@ struct KMajorCfg {
   static constexpr uint32_t LAYOUT = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;
 };
 
-template <int KC>
+// CS = cluster size. With CS > 1 the CS CTAs of a cluster work on CS consecutive pixel tiles of the same
+// output-channel tile in lock step; each loads 1/CS of the filter tile and multicasts it to all of them
+// (filter traffic from L2 drops by CS), and every MMA issuer releases a pipeline slot in ALL CTAs.
+template <int KC, int CS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvTcArgs args) {
@@ -80,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < args.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
@@ -94,18 +99,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive / copy
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   const int tiles_hw = args.tiles_w * args.tiles_h;
+  // cluster-tile schedule: cluster c takes cluster tiles c, c + #clusters, ...; cluster tile ct covers
+  // pixel tiles (ct / n_ntiles) * CS + rank of output-channel tile ct % n_ntiles
+  const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  const int num_ctiles = args.num_tiles / CS;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) ==============
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-      const int nt = tile % args.n_ntiles;
-      const int mt = tile / args.n_ntiles;
+    const int bslice = args.BN / CS;                           // filter rows this CTA loads
+    const uint32_t bslice_bytes = (uint32_t)bslice * KC * 2u;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * CS + crank;
       const int w0 = (mt % args.tiles_w) * args.bw;
       const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
       const int n0 = (mt / tiles_hw) * args.bn;
@@ -121,7 +136,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* b_dst = a_dst + args.a_bytes;
             mbar_expect_tx(&full_bar[s], args.tx_bytes);
             tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw, ch, cn);
-            tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
+            if (CS == 1) {
+              tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
+            } else {
+              tma_load_2d_mcast(b_dst + (size_t)crank * bslice_bytes, &tmB, &full_bar[s], wc + kc * KC,
+                                nt * args.BN + crank * bslice, cmask);
+            }
           }
           __syncwarp();
           if (++s == args.stages) { s = 0; ph ^= 1; }
@@ -138,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     const int nk = args.taps.n * args.nkc;
-    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       mbar_wait(&tempty_bar[as], aph ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
@@ -154,7 +174,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16_ss(d_addr, smem_desc_join(alo + 2 * k, dhi), smem_desc_join(blo + 2 * k, dhi),
                          idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (CS == 1) umma_commit(&empty_bar[s]);
+          else umma_commit_mcast(&empty_bar[s], cmask);
           if (it == nk - 1) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
@@ -172,9 +193,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ni = m / (args.bw * args.bh);
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-      const int nt = tile % args.n_ntiles;
-      const int mt = tile / args.n_ntiles;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * CS + crank;
       const int w = (mt % args.tiles_w) * args.bw + wi;
       const int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
       const int n = (mt / tiles_hw) * args.bn + ni;
@@ -228,9 +249,221 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv_tc2_kernel: the same shifted-window GEMM on an SM PAIR (tcgen05 cta_group::2).
+// The pair computes a 256-pixel x BN tile: each CTA stages its own 128-pixel A tile and HALF of the
+// filter tile (BN/2 rows), the leader CTA issues M=256 MMAs that read both CTAs' shared memory, and each
+// CTA ends up with its own 128 x BN accumulator in its own TMEM. Per 128x160x16 of work an SM now moves
+// 4 KB (A) + 2.5 KB (B/2) in and out of shared memory instead of 4 + 5 KB: shared-memory bandwidth,
+// not L2, is what limited the single-CTA kernel (ncu: tensor pipe active 53 %, 150 cycles per MMA
+// against 144 cycles of shared-memory traffic).
+//   barriers: full[s] lives in the leader (both CTAs' TMA loads complete_tx on it); empty[s] / tfull[a]
+//   are local in each CTA and signalled by the leader's multicast tcgen05.commit; tempty[a] lives in the
+//   leader and collects the 8 epilogue warps of the pair.
+// -------------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvTcArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 8);
+    mbar_init(&tempty_bar[1], 8);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(&tmem_base_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int tiles_hw = args.tiles_w * args.tiles_h;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_ptiles = args.num_tiles >> 1;  // pair tiles
+  const int bhalf = args.BN >> 1;
+
+  const int nk = args.taps.n * args.nkc;                    // K-blocks per tile
+  const int nst = (nk + args.gblk - 1) / args.gblk;         // pipeline stages per tile
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    // a stage holds up to gblk K-blocks (any mix of taps / channel chunks), one barrier round trip
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int w0 = (mt % args.tiles_w) * args.bw;
+      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
+      const int n0 = (mt / tiles_hw) * args.bn;
+      for (int st = 0; st < nst; ++st) {
+        const int blk0 = st * args.gblk;
+        const int cnt = min(args.gblk, nk - blk0);
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* base = smem + (size_t)s * args.stage_bytes;
+          const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)cnt * args.tx_bytes);
+          for (int g = 0; g < cnt; ++g) {
+            const int blk = blk0 + g;
+            const int t = blk / args.nkc;
+            const int kc = blk - t * args.nkc;
+            uint8_t* a_dst = base + (size_t)g * args.block_bytes;
+            tma_load_4d_2sm(a_dst, &tmA, full_leader, kc * KC, w0 + args.taps.dw[t],
+                            h0 + args.taps.dh[t], n0 + args.taps.dn[t]);
+            tma_load_2d_2sm(a_dst + args.a_bytes, &tmB, full_leader, args.taps.wcol[t] + kc * KC,
+                            nt * args.BN + crank * bhalf);
+          }
+        }
+        __syncwarp();
+        if (++s == args.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      const uint32_t idesc = make_idesc_bf16(256, args.BN, 0, 0);
+      const uint32_t dhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t blk_step = args.block_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
+        for (int st = 0; st < nst; ++st) {
+          const int cnt = min(args.gblk, nk - st * args.gblk);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
+            uint32_t alo = smem_desc_lo(a_addr, 16);
+            uint32_t blo = smem_desc_lo(a_addr + args.a_bytes, 16);
+            uint32_t acc = st != 0 ? 1u : 0u;
+            for (int g = 0; g < cnt; ++g) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                umma_bf16_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, dhi),
+                                 smem_desc_join(blo + 2 * k, dhi), idesc, acc);
+                acc = 1u;
+              }
+              alo += blk_step;
+              blo += blk_step;
+            }
+            umma_commit_2sm_mcast(&empty_bar[s], 3);
+            if (st == nst - 1) umma_commit_2sm_mcast(&tfull_bar[as], 3);
+          }
+          __syncwarp();
+          if (++s == args.stages) { s = 0; ph ^= 1; }
+        }
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own TMEM, own pixel tile) =====================
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const int wi = m % args.bw;
+    const int hi = (m / args.bw) % args.bh;
+    const int ni = m / (args.bw * args.bh);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int w = (mt % args.tiles_w) * args.bw + wi;
+      const int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
+      const int n = (mt / tiles_hw) * args.bn + ni;
+      const bool valid = (m < args.rows_valid) && (w < args.Q) && (h < args.P) && (n < args.Nimg);
+      const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
+      const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
+      bf16* orow = args.out + off;
+      const bf16* rrow = args.residual ? args.residual + off : nullptr;
+      const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
+      for (int c = 0; c < args.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (brow) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
+          }
+          if (rrow) {
+            Vec8 r0, r1;
+            r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
+            r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
+            float rf[16];
+            r0.to_float(rf);
+            r1.to_float(rf + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+          }
+          Vec8 o0, o1;
+          o0.from_float(f);
+          o1.from_float(f + 8);
+          *reinterpret_cast<uint4*>(orow + c) = o0.raw;
+          *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
