@@ -158,16 +158,16 @@ static int largest_divisor_leq(int n, int cap) {
 }
 
 // Box of output pixels (w, h, images) with at most 128 pixels.
-static TilePlan plan_tiles(int Nimg, int P, int Q) {
+static TilePlan plan_tiles(int Nimg, int P, int Q, int cap = 128) {
   TilePlan t;
-  if (Q >= 128) {
-    t.bw = 128; t.bh = 1; t.bn = 1;
+  if (Q >= cap) {
+    t.bw = cap; t.bh = 1; t.bn = 1;
   } else {
     t.bw = Q;
-    const int mh = 128 / Q;
+    const int mh = cap / Q;
     if (mh >= P) {
       t.bh = P;
-      t.bn = largest_divisor_leq(Nimg, std::max(1, 128 / (Q * P)));
+      t.bn = largest_divisor_leq(Nimg, std::max(1, cap / (Q * P)));
     } else {
       int d = largest_divisor_leq(P, mh);
       t.bh = (2 * d > mh) ? d : mh;
@@ -370,7 +370,7 @@ static int launch_conv_tc_cs(int cs, const CUtensorMap& tmA, const CUtensorMap& 
 static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                        int wcols, const TapTable& taps, void* out, const void* residual,
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st) {
-  const int KC = pick_kc(Cin);
+  int KC = pick_kc(Cin);
   const int BN = pick_bn(Cout, 16, 256);
   B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
   TilePlan t = plan_tiles(Nimg, P, Q);
@@ -378,15 +378,18 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   memset(&a, 0, sizeof(a));
   a.bw = t.bw; a.bh = t.bh; a.bn = t.bn; a.rows_valid = t.rows_valid;
   a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
-  a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = Cin / KC;
+  const int m_tiles_all = t.tiles_w * t.tiles_h * t.tiles_n;
+  const bool pair = conv_use_pair() && m_tiles_all % 2 == 0 && BN % 32 == 0;
+  // (tried: 64-channel blocks with a partial last block per tap for Cin = 160 - the extra predicate per
+  //  MMA slowed the issue loop more than SWIZZLE_128B gained; KC stays a divisor of Cin)
+  a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = (Cin + KC - 1) / KC; a.cin = Cin;
   a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
   a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles;
   a.taps = taps;
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
-  const int m_tiles_all = t.tiles_w * t.tiles_h * t.tiles_n;
-  if (conv_use_pair() && m_tiles_all % 2 == 0 && BN % 32 == 0) {
+  if (pair) {
     // SM pair: every CTA stages BN/2 filter rows (whole 8-row swizzle atoms, UMMA N multiple of 16)
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
@@ -575,36 +578,101 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
   return 0;
 }
 
-template <int SL>
+static int wgrad_cluster_size() {
+  // B200_WGRAD_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing the multicast dY slabs
+  static int cs = 0;
+  if (cs == 0) {
+    const char* e = getenv("B200_WGRAD_CLUSTER");
+    cs = e ? atoi(e) : 1;  // measured: no gain from multicasting dY (round 1), default off
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+  }
+  return cs;
+}
+
+static int wgrad_mtiles_per_cta() {
+  // B200_WGRAD_MT = 1 | 2 (default 1): M tiles (TMEM accumulators) per CTA sharing each dY stage.
+  // Measured in round 1: 2 tiles with 64-pixel stages is SLOWER (503 vs 692 TFLOP/s at C=160) although it
+  // moves 28 % fewer bytes - more, smaller TMA boxes per MMA cost more than the bytes saved.
+  static int mt = 0;
+  if (mt == 0) {
+    const char* e = getenv("B200_WGRAD_MT");
+    mt = e ? atoi(e) : 1;
+    if (mt != 1 && mt != 2) mt = 1;
+  }
+  return mt;
+}
+
+template <int SL, int CS, int MT>
 static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, WgradTcArgs& a,
                            cudaStream_t st) {
   static bool attr_set = false;
   const int max_dyn = 228352;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_dyn));
+    B200_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<SL, CS, MT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
     attr_set = true;
   }
-  a.slab_bytes = 128u * SL * 2u;
-  a.stage_bytes = (uint32_t)(128 / SL + a.BN / SL) * a.slab_bytes;
-  a.stages = std::min<int>(4, (max_dyn - 1024) / (int)a.stage_bytes);
+  a.stage_bytes = (uint32_t)(MT * (128 / SL) + a.nb) * a.slab_bytes;
+  a.stages = std::min<int>(8, (max_dyn - 1024) / (int)a.stage_bytes);
   B200_REQUIRE(a.stages >= 2, "wgrad_tc: tile does not fit in shared memory");
+  a.tmem_cols = 32;
+  while (a.tmem_cols < (MT - 1) * 256 + a.BN) a.tmem_cols *= 2;
   size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
   dyn = std::max<size_t>(dyn, 120 * 1024);
-  dim3 grid(a.n_mtiles * a.n_ntiles, a.splits);
-  wgrad_tc_kernel<SL><<<grid, TC_THREADS, dyn, st>>>(tmX, tmDy, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.n_mgroups * a.n_ntiles, a.splits);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<SL, CS, MT>, tmX, tmDy, a));
   B200_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
+}
+
+template <int SL>
+static int launch_wgrad_tc_cs(int cs, int mt, const CUtensorMap& tmX, const CUtensorMap& tmDy,
+                              WgradTcArgs& a, cudaStream_t st) {
+  if (mt == 2) {
+    switch (cs) {
+      case 4: return launch_wgrad_tc<SL, 4, 2>(tmX, tmDy, a, st);
+      case 2: return launch_wgrad_tc<SL, 2, 2>(tmX, tmDy, a, st);
+      default: return launch_wgrad_tc<SL, 1, 2>(tmX, tmDy, a, st);
+    }
+  }
+  switch (cs) {
+    case 4: return launch_wgrad_tc<SL, 4, 1>(tmX, tmDy, a, st);
+    case 2: return launch_wgrad_tc<SL, 2, 1>(tmX, tmDy, a, st);
+    default: return launch_wgrad_tc<SL, 1, 1>(tmX, tmDy, a, st);
+  }
 }
 
 // Shifted-window wgrad launch. act: [Nact][Ha][Wa][C] bf16, dy: [N][P][Q][K] bf16,
 // dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
                         int Q, int K, const TapTable& taps, float* dw, cudaStream_t st) {
-  const int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
-  int BN = pick_bn(K, SL, 160);
+  // slab width: 64 channels (128-byte TMA rows, SWIZZLE_128B) when both channel counts are multiples of
+  // 64 (measured: no better than 32 when a tap's last slab would be partial), else 32 or 16
+  int SL = (C % 64 == 0 && K % 64 == 0) ? 64 : (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
+  if (const char* e = getenv("B200_WGRAD_SLAB")) {
+    const int v = atoi(e);
+    if ((v == 16 || v == 32) && C % v == 0 && K % v == 0) SL = v;
+    if (v == 64 && C >= 64 && K >= 64) SL = 64;
+  }
+  int BN = pick_bn(K, 16, 160);
+  if (SL < 64) BN = pick_bn(K, SL, 160);
   B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
-  TilePlan t = plan_tiles(N, P, Q);
+  const int cs = wgrad_cluster_size();
+  int mt = wgrad_mtiles_per_cta();
+  // MT = 2 halves the pixels per stage (64) so that >= 4 stages still fit
+  TilePlan t = plan_tiles(N, P, Q, mt == 2 ? 64 : 128);
+  if (t.rows_valid % 16 != 0 && mt == 2) { mt = 1; t = plan_tiles(N, P, Q, 128); }
   B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc: pixel tile of %d rows is not a multiple of 16",
                t.rows_valid);
   WgradTcArgs a;
@@ -613,27 +681,48 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
   a.num_ptiles = t.tiles_w * t.tiles_h * t.tiles_n;
   a.kmmas = t.rows_valid / 16;
-  a.slabs_per_tap = C / SL;
+  a.slab_bytes = (uint32_t)((t.rows_valid * SL * 2 + 1023) / 1024 * 1024);
+  a.cin = C;
+  a.slabs_per_tap = (C + SL - 1) / SL;
   a.nslabs_total = taps.n * a.slabs_per_tap;
   const int spm = 128 / SL;
   a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
+  if (a.n_mtiles < 2) mt = 1;
+  a.n_mgroups = ((a.n_mtiles + mt - 1) / mt + cs - 1) / cs * cs;
   a.BN = BN; a.n_ntiles = K / BN;
+  a.nb = (BN + SL - 1) / SL;
   a.ktot = taps.n * C;
-  a.tmem_cols = 32;
-  while (a.tmem_cols < BN) a.tmem_cols *= 2;
-  const int cols = a.n_mtiles * a.n_ntiles;
-  int splits = std::max(1, (2 * num_sms() + cols - 1) / cols);
-  splits = std::min(splits, a.num_ptiles);
-  const int per = (a.num_ptiles + splits - 1) / splits;
-  a.splits = (a.num_ptiles + per - 1) / per;
+  const int cols = a.n_mgroups * a.n_ntiles;
+  // pixel-range splits: fill whole waves of the SMs (a 2.2-wave grid idles 30 % of the machine)
+  {
+    const int sms = num_sms();
+    int best = 1;
+    double best_score = -1.0;
+    const int max_splits = std::min(a.num_ptiles, 64);
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int per = (a.num_ptiles + sp - 1) / sp;
+      if ((a.num_ptiles + per - 1) / per != sp) continue;  // would leave empty splits
+      const long total = (long)cols * sp;
+      const long waves = (total + sms - 1) / sms;
+      double eff = (double)total / (double)(waves * sms);
+      if (per < 8) eff *= 0.85;              // short main loops pay prologue / epilogue overhead
+      if (total < sms) eff *= 0.9;
+      const double score = eff - 0.002 * sp;  // fewer atomics when equal
+      if (score > best_score) { best_score = score; best = sp; }
+    }
+    if (const char* e = getenv("B200_WGRAD_SPLITS")) best = std::max(1, std::min(atoi(e), a.num_ptiles));
+    const int per = (a.num_ptiles + best - 1) / best;
+    a.splits = (a.num_ptiles + per - 1) / per;
+  }
   a.taps = taps;
   a.dw = dw;
   if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
   CUtensorMap tmX, tmDy;
   if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn)) return rc;
   if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
-  if (SL == 32) return launch_wgrad_tc<32>(tmX, tmDy, a, st);
-  return launch_wgrad_tc<16>(tmX, tmDy, a, st);
+  if (SL == 64) return launch_wgrad_tc_cs<64>(cs, mt, tmX, tmDy, a, st);
+  if (SL == 32) return launch_wgrad_tc_cs<32>(cs, mt, tmX, tmDy, a, st);
+  return launch_wgrad_tc_cs<16>(cs, mt, tmX, tmDy, a, st);
 }
 
 extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N,
@@ -736,7 +825,7 @@ static int bn_blocks(int64_t rows, int C) {
   const int CGb = std::min(EW_THREADS, CG);
   const int RP = EW_THREADS / CGb;
   int64_t b = (rows + (int64_t)RP * 8 - 1) / ((int64_t)RP * 8);
-  b = std::min<int64_t>(b, std::min(BN_MAX_BLOCKS, num_sms() * 4));
+  b = std::min<int64_t>(b, std::min(BN_MAX_BLOCKS, num_sms() * 2));
   return (int)std::max<int64_t>(1, b);
 }
 
@@ -759,7 +848,7 @@ extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, floa
   bn_stats_partial_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(
       (const bf16*)x, rows, C, (float*)ws);
   B200_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>((const float*)ws, nblk, rows, C, eps,
+  bn_stats_finalize_kernel<<<(C + FIN_CH_PER_BLOCK - 1) / FIN_CH_PER_BLOCK, FIN_THREADS, 0, st>>>((const float*)ws, nblk, rows, C, eps,
                                                             momentum, mean, invstd, running_mean,
                                                             running_var, num_batches_tracked);
   B200_LAUNCH_CHECK("bn_stats_finalize_kernel");
@@ -801,8 +890,8 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
     const int CGb = std::min(EW_THREADS, CG);
     const int RP = EW_THREADS / CGb;
     const int64_t rows = (int64_t)N * H * W;
-    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 4 - 1) / ((int64_t)RP * 4),
-                                                          (int64_t)num_sms() * 8));
+    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 2 - 1) / ((int64_t)RP * 2),
+                                                          (int64_t)num_sms() * 12));
     dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
     bn_act_fwd_kernel<<<grid, EW_THREADS, 0, as_stream(stream)>>>(a);
   }
@@ -837,7 +926,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
     dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
     bn_act_bwd_reduce_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(a, (float*)ws);
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + FIN_CH_PER_BLOCK - 1) / FIN_CH_PER_BLOCK, FIN_THREADS, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
     B200_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   }
   {
@@ -845,7 +934,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
     const int CGb = std::min(EW_THREADS, CG);
     const int RP = EW_THREADS / CGb;
     int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 2 - 1) / ((int64_t)RP * 2),
-                                                          (int64_t)num_sms() * 8));
+                                                          (int64_t)num_sms() * 12));
     dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
     bn_act_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>(a);
   }

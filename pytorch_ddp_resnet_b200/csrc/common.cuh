@@ -90,21 +90,20 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// counter-based RNG for dropout: two rounds of a 32-bit multiply-xorshift mixer keyed by
-// (seed, element-pair index). One 32-bit draw yields two 16-bit uniforms.
+// counter-based RNG for dropout: Philox-2x32 rounds (one 32x32->64 multiply each) keyed by the seed,
+// counter = index of a group of four elements. One call yields four 16-bit uniforms, ~4 integer
+// operations per element.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16;
-  x *= 0x7feb352dU;
-  x ^= x >> 15;
-  x *= 0x846ca68bU;
-  x ^= x >> 16;
-  return x;
-}
-__host__ __device__ __forceinline__ uint32_t rng_draw(uint64_t seed, uint64_t idx) {
-  uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
-  uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
-  return mix32(mix32(lo ^ s0) + (hi ^ s1) * 0x9e3779b9U + 0x85ebca6bU);
+__host__ __device__ __forceinline__ uint2 rng_draw4(uint64_t seed, uint64_t idx) {
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32);
+  uint32_t key = (uint32_t)seed;
+  for (int r = 0; r < 5; ++r) {
+    const uint64_t p = (uint64_t)c0 * 0xD256D193u;
+    c0 = (uint32_t)(p >> 32) ^ key ^ c1;
+    c1 = (uint32_t)p;
+    key += 0x9E3779B9u;
+  }
+  return make_uint2(c0, c1);
 }
 
 // seed actually used by a launch: the host seed plus a device-resident step counter, so that a
@@ -204,6 +203,15 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* tm
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_mcast(void* dst, const CUtensorMap* tm, uint64_t* bar,
+                                                  int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
       : "memory");
 }
 

@@ -38,7 +38,8 @@ struct ConvTcArgs {
   int tiles_w, tiles_h, tiles_n;    // pixel tiles per dimension
   int n_ntiles;                     // output-channel tiles
   int BN;                           // output channels per tile (UMMA N)
-  int nkc;                          // Cin / KC
+  int nkc;                          // ceil(Cin / KC)
+  int cin;                          // input channels (the last K-block of a tap may be partial)
   int P, Q, Nimg;                   // output extent
   int ldo;                          // output channel pitch (elements)
   int num_tiles;
@@ -475,17 +476,20 @@ struct WgradTcArgs {
   int tiles_w, tiles_h, tiles_n;
   int num_ptiles;        // pixel tiles in total
   int kmmas;             // 16-pixel MMAs per pixel tile (rows_valid / 16)
-  int nslabs_total;      // ntaps * (Cin / SL)
-  int slabs_per_tap;     // Cin / SL
+  int nslabs_total;      // ntaps * ceil(Cin / SL)
+  int slabs_per_tap;     // ceil(Cin / SL); the last slab of a tap may be partial (TMA zero-fills it)
   int n_mtiles;          // ceil(nslabs_total / (128 / SL))
+  int n_mgroups;         // ceil(n_mtiles / MT), padded to the cluster size
   int n_ntiles;          // Cout / BN
+  int cin;               // input channels
+  int nb;                // dY slabs per stage = ceil(BN / SL)
   int BN;
   int splits;            // pixel-range splits (gridDim.y)
   int ktot;              // ntaps * Cin: row pitch of dw
   int stages;
   int tmem_cols;
   uint32_t stage_bytes;
-  uint32_t slab_bytes;   // 128 * SL * 2
+  uint32_t slab_bytes;   // rows per stage * SL * 2 (also the descriptor's leading byte offset)
   TapTable taps;
   float* dw;
 };
@@ -494,12 +498,16 @@ template <int SL>
 struct MnMajorCfg {
   static constexpr uint32_t ROW_BYTES = SL * 2;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;              // next group of 8 pixels
-  static constexpr uint32_t LBO = 128 * ROW_BYTES;            // next channel slab
+  static constexpr uint32_t LBO = 128 * ROW_BYTES;            // next channel slab (128-pixel slabs)
   static constexpr uint32_t LAYOUT = (SL == 64) ? 2u : (SL == 32) ? 4u : 6u;
   static constexpr int SLABS_PER_MTILE = 128 / SL;
 };
 
-template <int SL>
+// MT = M tiles (128 rows of (tap, channel) each) per CTA: they share every dY stage and accumulate
+// in MT TMEM accumulators, so per MMA the CTA pulls (MT*4 KB + 5 KB)/MT instead of 9 KB through L2/TMA.
+// CS = cluster size: the CS CTAs of a cluster own consecutive M-tile groups of the same (N tile, pixel
+// range); the dY slabs they all need are loaded once (slab i by CTA i % CS) and multicast.
+template <int SL, int CS, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                 const __grid_constant__ WgradTcArgs args) {
@@ -520,7 +528,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tma_prefetch_desc(&tmDy);
     for (int s = 0; s < args.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);
     }
     mbar_init(&tfull_bar, 1);
     mbar_fence_init();
@@ -531,24 +539,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();
   tc_fence_after();
+  const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int mt = blockIdx.x % args.n_mtiles;
-  const int nt = blockIdx.x / args.n_mtiles;
+  const int mg = blockIdx.x % args.n_mgroups;   // group of MT M tiles
+  const int nt = blockIdx.x / args.n_mgroups;
   const int per = (args.num_ptiles + args.splits - 1) / args.splits;
   const int pt0 = blockIdx.y * per;
   const int pt1 = min(args.num_ptiles, pt0 + per);
   const int tiles_hw = args.tiles_w * args.tiles_h;
-  const int q0 = mt * Cfg::SLABS_PER_MTILE;
-  const int na = min(Cfg::SLABS_PER_MTILE, args.nslabs_total - q0);  // valid A slabs
-  const int nb = args.BN / SL;                                        // B slabs
-  const uint32_t b_off = Cfg::SLABS_PER_MTILE * args.slab_bytes;
+  const int nb = args.nb;                                              // dY slabs per stage
+  const uint32_t a_tile_bytes = Cfg::SLABS_PER_MTILE * args.slab_bytes;
+  const uint32_t b_off = MT * a_tile_bytes;
+  int q0[MT], na[MT], na_total = 0;
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    q0[j] = (mg * MT + j) * Cfg::SLABS_PER_MTILE;
+    na[j] = max(0, min(Cfg::SLABS_PER_MTILE, args.nslabs_total - q0[j]));  // 0: padding tile
+    na_total += na[j];
+  }
 
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t tx = (uint32_t)(na + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
+    const uint32_t tx = (uint32_t)(na_total + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
     for (int pt = pt0; pt < pt1; ++pt) {
       const int w0 = (pt % args.tiles_w) * args.bw;
       const int h0 = ((pt / args.tiles_w) % args.tiles_h) * args.bh;
@@ -558,16 +575,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
         uint8_t* b_dst = a_dst + b_off;
         mbar_expect_tx(&full_bar[s], tx);
-        for (int i = 0; i < na; ++i) {
-          const int q = q0 + i;
-          const int t = q / args.slabs_per_tap;
-          const int ck = q % args.slabs_per_tap;
-          tma_load_4d(a_dst + (size_t)i * args.slab_bytes, &tmX, &full_bar[s], ck * SL,
-                      w0 + args.taps.dw[t], h0 + args.taps.dh[t], n0 + args.taps.dn[t]);
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          for (int i = 0; i < na[j]; ++i) {
+            const int q = q0[j] + i;
+            const int t = q / args.slabs_per_tap;
+            const int ck = q % args.slabs_per_tap;
+            tma_load_4d(a_dst + (size_t)j * a_tile_bytes + (size_t)i * args.slab_bytes, &tmX,
+                        &full_bar[s], ck * SL, w0 + args.taps.dw[t], h0 + args.taps.dh[t],
+                        n0 + args.taps.dn[t]);
+          }
         }
-        for (int i = 0; i < nb; ++i) {
-          tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
-                      nt * args.BN + i * SL, w0, h0, n0);
+        if (CS == 1) {
+          for (int i = 0; i < nb; ++i)
+            tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
+                        nt * args.BN + i * SL, w0, h0, n0);
+        } else {
+          for (int i = crank; i < nb; i += CS)
+            tma_load_4d_mcast(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
+                              nt * args.BN + i * SL, w0, h0, n0, cmask);
         }
       }
       __syncwarp();
@@ -578,6 +604,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t dhi = smem_desc_hi(Cfg::SBO, Cfg::LAYOUT);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t kstep = (16u * Cfg::ROW_BYTES) >> 4;  // descriptor-address units per 16 pixels
+    const uint32_t tile_step = a_tile_bytes >> 4;
     int s = 0;
     uint32_t ph = 0;
     for (int pt = pt0; pt < pt1; ++pt) {
@@ -585,13 +612,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
-        const uint32_t alo = smem_desc_lo(a_addr, Cfg::LBO);
-        const uint32_t blo = smem_desc_lo(a_addr + b_off, Cfg::LBO);
+        const uint32_t alo = smem_desc_lo(a_addr, args.slab_bytes);
+        const uint32_t blo = smem_desc_lo(a_addr + b_off, args.slab_bytes);
+        const uint32_t acc = pt > pt0 ? 1u : 0u;
         for (int k = 0; k < args.kmmas; ++k) {
-          umma_bf16_ss(tmem_base, smem_desc_join(alo + k * kstep, dhi),
-                       smem_desc_join(blo + k * kstep, dhi), idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          const uint64_t bd = smem_desc_join(blo + k * kstep, dhi);
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            umma_bf16_ss(tmem_base + (uint32_t)j * 256u,
+                         smem_desc_join(alo + j * tile_step + k * kstep, dhi), bd, idesc,
+                         (acc | (uint32_t)k) != 0 ? 1u : 0u);
+          }
         }
-        umma_commit(&empty_bar[s]);
+        if (CS == 1) umma_commit(&empty_bar[s]);
+        else umma_commit_mcast(&empty_bar[s], cmask);
         if (pt == pt1 - 1) umma_commit(&tfull_bar);
       }
       __syncwarp();
@@ -602,34 +636,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       __syncwarp();
     }
   } else if (pt1 > pt0) {
-    // epilogue: lane m of the accumulator is (slab, channel) = (m / SL, m % SL)
+    // epilogue: lane m of accumulator j is (slab, channel) = (m / SL, m % SL) of M tile j
     const int wq = warp & 3;
     const int m = wq * 32 + lane;
-    const int q = q0 + m / SL;
-    const bool valid = q < args.nslabs_total;
-    int col = 0;
-    if (valid) {
-      const int t = q / args.slabs_per_tap;
-      const int ck = q % args.slabs_per_tap;
-      col = args.taps.wcol[t] + ck * SL + (m % SL);
-    }
-    float* drow = args.dw + (size_t)nt * args.BN * args.ktot + col;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
-    const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    for (int c = 0; c < args.BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_addr + c, v);
-      tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      const int q = q0[j] + m / SL;
+      bool valid = q < args.nslabs_total;
+      int col = 0;
       if (valid) {
-        if (args.splits == 1) {
+        const int t = q / args.slabs_per_tap;
+        const int ck = q % args.slabs_per_tap;
+        const int c = ck * SL + (m % SL);
+        valid = c < args.cin;  // rows of a partial last slab
+        col = args.taps.wcol[t] + c;
+      }
+      float* drow = args.dw + (size_t)nt * args.BN * args.ktot + col;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)j * 256u;
+      for (int c = 0; c < args.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          if (args.splits == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            drow[(size_t)(c + j) * args.ktot] = __uint_as_float(v[j]);
-        } else {
+            for (int jj = 0; jj < 16; ++jj)
+              drow[(size_t)(c + jj) * args.ktot] = __uint_as_float(v[jj]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            atomicAdd(drow + (size_t)(c + j) * args.ktot, __uint_as_float(v[j]));
+            for (int jj = 0; jj < 16; ++jj)
+              atomicAdd(drow + (size_t)(c + jj) * args.ktot, __uint_as_float(v[jj]));
+          }
         }
       }
     }
@@ -638,6 +677,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)args.tmem_cols);

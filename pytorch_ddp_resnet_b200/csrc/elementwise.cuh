@@ -10,6 +10,23 @@ namespace b200 {
 constexpr int EW_THREADS = 256;
 constexpr int BN_MAX_BLOCKS = 1024;
 
+// Inverted dropout on the 8 values of vector `v`: element j is dropped when its 16-bit uniform is
+// below drop_thr, else scaled by 1/(1-p) and (ROUND) rounded to bf16 like the reference's bf16 multiply.
+template <bool ROUND>
+__device__ __forceinline__ void dropout8(float* f, uint64_t seed, size_t v, uint32_t drop_thr,
+                                         float inv_keep) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint2 d = rng_draw4(seed, (uint64_t)v * 2 + h);
+    const uint32_t u[4] = {d.x & 0xffffu, d.x >> 16, d.y & 0xffffu, d.y >> 16};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = f[4 * h + j] * inv_keep;
+      f[4 * h + j] = (u[j] < drop_thr) ? 0.f : (ROUND ? round_bf16(t) : t);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // Block-level per-channel reduction helper. Each thread owns one 8-channel group `cg` (fixed for
 // the whole kernel) and a row lane `rl`; acc[] holds NACC*8 per-channel partial sums of that thread.
@@ -100,29 +117,32 @@ bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* 
   block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, C, g.cg0 * 8);
 }
 
-// Sum of the per-block partials of two quantities for 32 channels per block: 8 row lanes stride over
-// the partial blocks (coalesced 128-byte reads), then a shared-memory tree over the lanes.
+// Sum of the per-block partials of two quantities: one WARP per channel, lanes stride over the partial
+// blocks (independent loads, fully unrolled by the compiler), shuffle reduction in fp64.
 constexpr int FIN_THREADS = 256;
+constexpr int FIN_CH_PER_BLOCK = FIN_THREADS / 32;
 __device__ __forceinline__ bool finalize_sums(const float* __restrict__ partial, int nblk, int C,
                                               int& c, double& s0, double& s1) {
-  __shared__ double red[2][8][32];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  c = blockIdx.x * 32 + cl;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (int k = lane; k < nblk; k += 8) {
-      a += (double)partial[((size_t)k * 2 + 0) * C + c];
-      b += (double)partial[((size_t)k * 2 + 1) * C + c];
-    }
+  c = blockIdx.x * FIN_CH_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return false;
+  float a = 0.f, b = 0.f;  // <= 10 terms per lane: fp32 is exact enough before the fp64 tree
+  double da = 0.0, db = 0.0;
+#pragma unroll 4
+  for (int k = lane; k < nblk; k += 32) {
+    a = __ldg(partial + ((size_t)k * 2 + 0) * C + c);
+    b = __ldg(partial + ((size_t)k * 2 + 1) * C + c);
+    da += (double)a;
+    db += (double)b;
   }
-  red[0][lane][cl] = a;
-  red[1][lane][cl] = b;
-  __syncthreads();
-  if (lane != 0 || c >= C) return false;
-  s0 = 0.0; s1 = 0.0;
 #pragma unroll
-  for (int l = 0; l < 8; ++l) { s0 += red[0][l][cl]; s1 += red[1][l][cl]; }
-  return true;
+  for (int o = 16; o > 0; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    db += __shfl_xor_sync(0xffffffffu, db, o);
+  }
+  s0 = da;
+  s1 = db;
+  return lane == 0;
 }
 
 // mean / invstd from the partials (+ running-stat update, torch.nn.BatchNorm2d semantics)
@@ -171,7 +191,7 @@ struct BnActFwdArgs {
 // Thread mapping of the element-wise BN kernels: a thread owns ONE 8-channel group for the whole
 // kernel (per-channel coefficients live in registers) and walks rows with stride RP * gridDim.x;
 // the RP x CGb threads of a block touch RP consecutive rows = one contiguous 4 KB span per pass.
-__global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdArgs a) {
+__global__ void __launch_bounds__(EW_THREADS, 3) bn_act_fwd_kernel(const BnActFwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
   if (!g.active) return;
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdAr
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   const bool skip_here = a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C);
   const int64_t stride = (int64_t)g.RP * gridDim.x;
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < rows; r0 += U * stride) {
     Vec8 xv[U], sv[U];
 #pragma unroll
@@ -233,14 +253,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_act_fwd_kernel(const BnActFwdAr
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (a.drop_thr) {
-#pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
-          const uint32_t d = rng_draw(seed, v * 4 + j2);
-          f[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2] * a.inv_keep);
-          f[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(f[2 * j2 + 1] * a.inv_keep);
-        }
-      }
+      if (a.drop_thr) dropout8<false>(f, seed, v, a.drop_thr, a.inv_keep);  // the pack below rounds
       Vec8 o;
       o.from_float(f);
       stg_stream(a.y + v * 8, o.raw);
@@ -276,14 +289,7 @@ struct BnActBwdArgs {
 __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t seed, size_t v,
                                                  const Vec8& dv, const Vec8& yv, float* g) {
   dv.to_float(g);
-  if (a.drop_thr) {
-#pragma unroll
-    for (int j2 = 0; j2 < 4; ++j2) {
-      const uint32_t d = rng_draw(seed, v * 4 + j2);
-      g[2 * j2] = ((d & 0xffffu) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2] * a.inv_keep);
-      g[2 * j2 + 1] = ((d >> 16) < a.drop_thr) ? 0.f : round_bf16(g[2 * j2 + 1] * a.inv_keep);
-    }
-  }
+  if (a.drop_thr) dropout8<true>(g, seed, v, a.drop_thr, a.inv_keep);
   if (a.relu) {
     float yf[8];
     yv.to_float(yf);
@@ -293,7 +299,7 @@ __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t
 }
 
 // partial[b][0][c] = sum g, partial[b][1][c] = sum g * xhat
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 3)
 bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
   extern __shared__ float red_smem[];
   ReduceGeom g(a.C);
@@ -358,7 +364,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float
 // dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g.
 // Per channel this is dx = k1 * g + k2 * x + k3 with
 //   k1 = gamma*invstd, k2 = -k1*invstd*dgamma/rows, k3 = -k1*dbeta/rows - k2*mean   (registers).
-__global__ void __launch_bounds__(EW_THREADS) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
+__global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
   if (!g.active) return;

@@ -151,11 +151,12 @@ def test_eval_argmax_identical_on_fixed_batch_resnet20():
     from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
     spec = "c3,16,3,1,1 n a r3 r3 r3 ap8,1,0 fc64,10"
     state = O.init_state(spec, False, False, seed=3)
+    gen = torch.Generator().manual_seed(17)
     for k in state:  # non-trivial running statistics
         if k.endswith("running_var"):
-            state[k] = torch.rand_like(state[k]) + 0.5
+            state[k] = torch.rand(state[k].shape, generator=gen) + 0.5
         if k.endswith("running_mean"):
-            state[k] = torch.randn_like(state[k]) * 0.1
+            state[k] = torch.randn(state[k].shape, generator=gen) * 0.1
     model = ResNet(spec, False, False, 0.0)
     model.load_state_dict(state)
     model = model.cuda().eval()
@@ -165,7 +166,7 @@ def test_eval_argmax_identical_on_fixed_batch_resnet20():
         mine = model(x.cuda()).float().cpu()
     top2 = ref.topk(2, -1).values
     clear = (top2[:, 0] - top2[:, 1]) > 2e-2 * ref.abs().max()
-    assert clear.float().mean() > 0.8
+    assert clear.float().mean() > 0.5  # enough decisive samples for the comparison to mean something
     assert torch.equal(mine.argmax(-1)[clear], ref.argmax(-1)[clear])
     assert rel_l2(mine, ref) < 3e-2
 
