@@ -590,14 +590,15 @@ static int wgrad_cluster_size() {
 }
 
 static int wgrad_mtiles_per_cta() {
-  // B200_WGRAD_MT = 1 | 2 (default 1): M tiles (TMEM accumulators) per CTA sharing each dY stage.
-  // Measured in round 1: 2 tiles with 64-pixel stages is SLOWER (503 vs 692 TFLOP/s at C=160) although it
-  // moves 28 % fewer bytes - more, smaller TMA boxes per MMA cost more than the bytes saved.
-  static int mt = 0;
-  if (mt == 0) {
+  // B200_WGRAD_MT = 0 (auto) | 1 | 2: M tiles (TMEM accumulators) per CTA sharing each dY stage.
+  // Measured in round 1 (after the producer's index math was hoisted): two tiles with 128-pixel stages
+  // reach 928 / 902 TFLOP/s at C = 160 / 320 against 818 / 751 with one tile (28 % fewer bytes per MMA
+  // through the TMA/L2 path), but 692 against 720 at C = 640, hence the auto rule in run_wgrad_tc.
+  static int mt = -1;
+  if (mt < 0) {
     const char* e = getenv("B200_WGRAD_MT");
-    mt = e ? atoi(e) : 1;
-    if (mt != 1 && mt != 2) mt = 1;
+    mt = e ? atoi(e) : 0;
+    if (mt < 0 || mt > 2) mt = 0;
   }
   return mt;
 }
@@ -614,6 +615,7 @@ static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, Wgra
   }
   a.stage_bytes = (uint32_t)(MT * (128 / SL) + a.nb) * a.slab_bytes;
   a.stages = std::min<int>(8, (max_dyn - 1024) / (int)a.stage_bytes);
+  if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
   B200_REQUIRE(a.stages >= 2, "wgrad_tc: tile does not fit in shared memory");
   a.tmem_cols = 32;
   while (a.tmem_cols < (MT - 1) * 256 + a.BN) a.tmem_cols *= 2;
@@ -657,9 +659,9 @@ static int launch_wgrad_tc_cs(int cs, int mt, const CUtensorMap& tmX, const CUte
 // dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
                         int Q, int K, const TapTable& taps, float* dw, cudaStream_t st) {
-  // slab width: 64 channels (128-byte TMA rows, SWIZZLE_128B) when both channel counts are multiples of
-  // 64 (measured: no better than 32 when a tap's last slab would be partial), else 32 or 16
-  int SL = (C % 64 == 0 && K % 64 == 0) ? 64 : (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
+  // slab width: 32 channels (64-byte TMA rows, SWIZZLE_64B) or 16; 64-channel slabs (SWIZZLE_128B, with
+  // partial last slabs) are implemented and tested but were not faster (round 1), B200_WGRAD_SLAB=64
+  int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
   if (const char* e = getenv("B200_WGRAD_SLAB")) {
     const int v = atoi(e);
     if ((v == 16 || v == 32) && C % v == 0 && K % v == 0) SL = v;
@@ -670,8 +672,10 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
   const int cs = wgrad_cluster_size();
   int mt = wgrad_mtiles_per_cta();
-  // MT = 2 halves the pixels per stage (64) so that >= 4 stages still fit
-  TilePlan t = plan_tiles(N, P, Q, mt == 2 ? 64 : 128);
+  if (mt == 0) mt = (C <= 320) ? 2 : 1;
+  int px_cap = 128;
+  if (const char* e = getenv("B200_WGRAD_PX")) px_cap = (atoi(e) == 64) ? 64 : 128;
+  TilePlan t = plan_tiles(N, P, Q, px_cap);
   if (t.rows_valid % 16 != 0 && mt == 2) { mt = 1; t = plan_tiles(N, P, Q, 128); }
   B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc: pixel tile of %d rows is not a multiple of 16",
                t.rows_valid);
@@ -688,6 +692,9 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   const int spm = 128 / SL;
   a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
   if (a.n_mtiles < 2) mt = 1;
+  a.BN = BN;
+  a.nb = (BN + SL - 1) / SL;
+  if (mt == 2 && 2 * (size_t)(2 * spm + a.nb) * a.slab_bytes > 228352 - 1024) mt = 1;  // needs 2 stages
   a.n_mgroups = ((a.n_mtiles + mt - 1) / mt + cs - 1) / cs * cs;
   a.BN = BN; a.n_ntiles = K / BN;
   a.nb = (BN + SL - 1) / SL;

@@ -563,13 +563,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
+    // Everything that does not depend on the pixel tile is hoisted out of the loop: the producer issues
+    // 9+ TMA copies per stage and was the bottleneck when it re-derived (tap, chunk) per copy with
+    // integer divisions (ncu: the MMA warp starved while the producer never waited for a free slot).
     int s = 0;
     uint32_t ph = 0;
     const uint32_t tx = (uint32_t)(na_total + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
+    int sc[MT][Cfg::SLABS_PER_MTILE], sw[MT][Cfg::SLABS_PER_MTILE], sh[MT][Cfg::SLABS_PER_MTILE],
+        sn[MT][Cfg::SLABS_PER_MTILE];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+#pragma unroll
+      for (int i = 0; i < Cfg::SLABS_PER_MTILE; ++i) {
+        const int q = min(q0[j] + i, args.nslabs_total - 1);
+        const int t = q / args.slabs_per_tap;
+        sc[j][i] = (q - t * args.slabs_per_tap) * SL;
+        sw[j][i] = args.taps.dw[t];
+        sh[j][i] = args.taps.dh[t];
+        sn[j][i] = args.taps.dn[t];
+      }
+    }
+    const int bc0 = nt * args.BN;
+    // pixel-tile coordinates advance incrementally (w fastest, then h, then image group)
+    int tw = pt0 % args.tiles_w;
+    int th = (pt0 / args.tiles_w) % args.tiles_h;
+    int tn = pt0 / tiles_hw;
     for (int pt = pt0; pt < pt1; ++pt) {
-      const int w0 = (pt % args.tiles_w) * args.bw;
-      const int h0 = ((pt / args.tiles_w) % args.tiles_h) * args.bh;
-      const int n0 = (pt / tiles_hw) * args.bn;
+      const int w0 = tw * args.bw, h0 = th * args.bh, n0 = tn * args.bn;
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
@@ -577,27 +598,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_expect_tx(&full_bar[s], tx);
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
-          for (int i = 0; i < na[j]; ++i) {
-            const int q = q0[j] + i;
-            const int t = q / args.slabs_per_tap;
-            const int ck = q % args.slabs_per_tap;
-            tma_load_4d(a_dst + (size_t)j * a_tile_bytes + (size_t)i * args.slab_bytes, &tmX,
-                        &full_bar[s], ck * SL, w0 + args.taps.dw[t], h0 + args.taps.dh[t],
-                        n0 + args.taps.dn[t]);
+#pragma unroll
+          for (int i = 0; i < Cfg::SLABS_PER_MTILE; ++i) {
+            if (i < na[j])
+              tma_load_4d(a_dst + (size_t)j * a_tile_bytes + (size_t)i * args.slab_bytes, &tmX,
+                          &full_bar[s], sc[j][i], w0 + sw[j][i], h0 + sh[j][i], n0 + sn[j][i]);
           }
         }
         if (CS == 1) {
           for (int i = 0; i < nb; ++i)
-            tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
-                        nt * args.BN + i * SL, w0, h0, n0);
+            tma_load_4d(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s], bc0 + i * SL, w0, h0,
+                        n0);
         } else {
           for (int i = crank; i < nb; i += CS)
-            tma_load_4d_mcast(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s],
-                              nt * args.BN + i * SL, w0, h0, n0, cmask);
+            tma_load_4d_mcast(b_dst + (size_t)i * args.slab_bytes, &tmDy, &full_bar[s], bc0 + i * SL,
+                              w0, h0, n0, cmask);
         }
       }
       __syncwarp();
       if (++s == args.stages) { s = 0; ph ^= 1; }
+      if (++tw == args.tiles_w) {
+        tw = 0;
+        if (++th == args.tiles_h) { th = 0; ++tn; }
+      }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, args.BN, 1, 1);
