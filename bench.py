@@ -36,6 +36,8 @@ BATCH_PER_GPU = 128
 SGD = dict(lr=0.1, momentum=0.9, dampening=0.0, nesterov=True, weight_decay=5e-4)
 WORKLOAD = "WRN-28-10 (dropout 0.3) CIFAR-10-shape 32x32 synthetic bf16 training, batch 128/GPU"
 METRIC = "train img/s WRN-28-10 CIFAR"
+# DRAM bytes per launch of the dominant kernel from the round's `ncu --set full` capture (profiles/)
+DOMINANT_KERNEL_DRAM_BYTES = 44.27e6
 
 
 def peaks():
@@ -312,8 +314,11 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16"], "traffic": None,
-                     "kernel": "conv_tc_kernel<32> fprop 3x3 s1 160->160 @32x32 batch 128 (60.4 GFLOP/launch)",
+                     "frac": achieved / pk["bf16"], "traffic": DOMINANT_KERNEL_DRAM_BYTES,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                       "(profiles/r01_conv_ncu_metrics.txt); algorithmic bytes 84.3e6",
+                     "kernel": "conv_tc2_kernel<32> (cta_group::2) fprop 3x3 s1 160->160 @32x32 batch 128 "
+                               "(60.4 GFLOP/launch)",
                      "kernel_ms": kms, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                      "step_conv_tflops": conv_tflops_in_step,
                      "step_conv_frac_of_sustained": conv_tflops_in_step / pk["bf16_sustained"]},
