@@ -181,6 +181,31 @@ static TilePlan plan_tiles(int Nimg, int P, int Q, int cap = 128) {
   return t;
 }
 
+// wgrad reduces over the pixels of a tile in 16-pixel MMAs: its tiles must hold a multiple of 16 rows.
+// Rows that fall outside the image are zero-filled by TMA in BOTH operands and add nothing, so tiles
+// may overhang (e.g. 14x8 tiles on a 14x14 map). Picks the box with the best useful-row fraction.
+static TilePlan plan_tiles_mult16(int Nimg, int P, int Q, int cap) {
+  TilePlan best = plan_tiles(Nimg, P, Q, cap);
+  if (best.rows_valid % 16 == 0) return best;
+  double best_eff = -1.0;
+  const int bw = std::min(Q, cap);
+  for (int bh = 1; bh <= std::max(1, cap / bw) && bh <= P + 15; ++bh) {
+    const int max_bn = (bh >= P) ? std::max(1, cap / (bw * bh)) : 1;
+    for (int bn = 1; bn <= std::min(max_bn, Nimg); ++bn) {
+      const int rows = bw * bh * bn;
+      if (rows > cap || rows % 16 != 0) continue;
+      const int th = (P + bh - 1) / bh, tn = (Nimg + bn - 1) / bn, tw = (Q + bw - 1) / bw;
+      const double eff = (double)Nimg * P * Q / ((double)th * tn * tw * cap);
+      if (eff > best_eff) {
+        best_eff = eff;
+        best.bw = bw; best.bh = bh; best.bn = bn; best.rows_valid = rows;
+        best.tiles_w = tw; best.tiles_h = th; best.tiles_n = tn;
+      }
+    }
+  }
+  return best;
+}
+
 static int pick_kc(int C) { return (C % 64 == 0) ? 64 : (C % 32 == 0) ? 32 : 16; }
 
 // largest divisor of K that is a multiple of `mult` and <= cap (0 if none)
@@ -208,7 +233,7 @@ extern "C" int b200_conv2d_tc_supported(int pass, int N, int H, int W, int C, in
   if (!same_geometry(H, W, R, S, stride, pad, &P, &Q)) return 0;
   if (C % 16 != 0 || K % 16 != 0) return 0;
   if (pass == B200_PASS_WGRAD) {
-    TilePlan t = plan_tiles(N, P, Q);
+    TilePlan t = plan_tiles_mult16(N, P, Q, 128);
     if (t.rows_valid % 16 != 0) return 0;
   }
   return 1;
@@ -225,7 +250,7 @@ static bool use_im2col(int algo, int pass, int N, int H, int W, int C, int K, in
   if (C >= 16 || K % 16 != 0 || R * S * C > 1024) return false;
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   if (P < 1 || Q < 1) return false;
-  if (pass == B200_PASS_WGRAD && plan_tiles(N, P, Q).rows_valid % 16 != 0) return false;
+  if (pass == B200_PASS_WGRAD && plan_tiles_mult16(N, P, Q, 128).rows_valid % 16 != 0) return false;
   return true;
 }
 
@@ -675,8 +700,8 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   if (mt == 0) mt = (C <= 320) ? 2 : 1;
   int px_cap = 128;
   if (const char* e = getenv("B200_WGRAD_PX")) px_cap = (atoi(e) == 64) ? 64 : 128;
-  TilePlan t = plan_tiles(N, P, Q, px_cap);
-  if (t.rows_valid % 16 != 0 && mt == 2) { mt = 1; t = plan_tiles(N, P, Q, 128); }
+  TilePlan t = plan_tiles_mult16(N, P, Q, px_cap);
+  if (t.rows_valid % 16 != 0 && mt == 2) { mt = 1; t = plan_tiles_mult16(N, P, Q, 128); }
   B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc: pixel tile of %d rows is not a multiple of 16",
                t.rows_valid);
   WgradTcArgs a;
@@ -1008,11 +1033,10 @@ extern "C" int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int
 
 extern "C" int b200_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H,
                                 int W, int C, int k, int stride, int pad, b200_stream_t stream) {
-  (void)y;
-  B200_REQUIRE(dy && x && dx && stride >= 1, "maxpool_bwd: bad arguments");
+  B200_REQUIRE(dy && x && y && dx && stride >= 1 && C % 8 == 0, "maxpool_bwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  maxpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)dy, (const bf16*)x, (bf16*)dx, d);
+  maxpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)y, (bf16*)dx, d);
   B200_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;
 }

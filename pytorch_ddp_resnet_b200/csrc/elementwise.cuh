@@ -695,20 +695,24 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
   }
 }
 
-// gather form of max-pool backward: an input element receives dy of every window whose first
-// maximum (row-major scan order, as torch's max_pool2d_with_indices) is that element.
+// Gather form of max-pool backward, 8 channels per thread: an input element receives dy of every
+// window whose FIRST maximum (row-major scan order, as torch's max_pool2d_with_indices) it is. The pooled
+// output y gives the window maximum; only the positions scanned before (h, w) are re-read to break ties.
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                   bf16* __restrict__ dx, PoolDims d) {
-  const size_t total = (size_t)d.N * d.H * d.W * d.C;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % d.C);
-    const size_t pix = idx / d.C;
+                                   const bf16* __restrict__ y, bf16* __restrict__ dx, PoolDims d) {
+  const int CG = d.C / 8;
+  const size_t nvec = (size_t)d.N * d.H * d.W * CG;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % CG);
+    const size_t pix = v / CG;
     const int w = (int)(pix % d.W);
     const int h = (int)((pix / d.W) % d.H);
     const int n = (int)(pix / ((size_t)d.W * d.H));
-    const float xv = __bfloat162float(x[idx]);
-    float acc = 0.f;
+    Vec8 xv;
+    xv.raw = ldg_stream(x + v * 8);
+    float xf[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    xv.to_float(xf);
     for (int r = 0; r < d.k; ++r) {
       const int hp = h + d.pad - r;
       if (hp < 0 || (hp % d.stride) != 0) continue;
@@ -719,23 +723,41 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const bf16* __re
         if (wp < 0 || (wp % d.stride) != 0) continue;
         const int q = wp / d.stride;
         if (q >= d.Q) continue;
-        // is (h, w) the first maximum of window (p, q)?
-        bool is_arg = true;
-        for (int r2 = 0; r2 < d.k && is_arg; ++r2) {
+        const size_t o = ((((size_t)n * d.P + p) * d.Q + q) * d.C) + (size_t)cg * 8;
+        Vec8 yv, gv;
+        yv.raw = ldg_stream(y + o);
+        float yf[8];
+        yv.to_float(yf);
+        bool cand[8], any = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cand[j] = xf[j] == yf[j]; any |= cand[j]; }
+        if (!any) continue;
+        // positions of window (p, q) scanned before (h, w): rows r2 < r, or the same row with s2 < s
+        for (int r2 = 0; r2 <= r; ++r2) {
           const int h2 = p * d.stride + r2 - d.pad;
           if (h2 < 0 || h2 >= d.H) continue;
-          for (int s2 = 0; s2 < d.k; ++s2) {
+          const int s_end = (r2 < r) ? d.k : s;
+          for (int s2 = 0; s2 < s_end; ++s2) {
             const int w2 = q * d.stride + s2 - d.pad;
             if (w2 < 0 || w2 >= d.W) continue;
-            const float o = __bfloat162float(x[(((size_t)n * d.H + h2) * d.W + w2) * d.C + c]);
-            const bool before = (h2 < h) || (h2 == h && w2 < w);
-            if (o > xv || (before && o == xv)) { is_arg = false; break; }
+            Vec8 ov;
+            ov.raw = ldg_stream(x + (((size_t)n * d.H + h2) * d.W + w2) * d.C + (size_t)cg * 8);
+            float of[8];
+            ov.to_float(of);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cand[j] = cand[j] && (of[j] != yf[j]);
           }
         }
-        if (is_arg) acc += __bfloat162float(dy[(((size_t)n * d.P + p) * d.Q + q) * d.C + c]);
+        gv.raw = ldg_stream(dy + o);
+        float gf[8];
+        gv.to_float(gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += cand[j] ? gf[j] : 0.f;
       }
     }
-    dx[idx] = __float2bfloat16_rn(acc);
+    Vec8 ov;
+    ov.from_float(acc);
+    stg_stream(dx + v * 8, ov.raw);
   }
 }
 

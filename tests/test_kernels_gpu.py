@@ -49,6 +49,12 @@ CONV_SHAPES = [
     (2, 32, 32, 16, 32, 3, 2, 1),
     (6, 8, 8, 32, 48, 3, 1, 1),
     (3, 16, 16, 48, 32, 3, 1, 1),
+    # ImageNet-style feature maps whose rows do not tile 128 pixels evenly (partial / overhanging tiles)
+    (2, 56, 56, 64, 64, 3, 1, 1),
+    (3, 28, 28, 64, 128, 1, 1, 0),
+    (3, 14, 14, 128, 128, 3, 1, 1),
+    (5, 7, 7, 256, 128, 3, 1, 1),
+    (2, 28, 28, 64, 64, 3, 2, 1),
 ]
 
 
