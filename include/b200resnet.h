@@ -60,6 +60,10 @@ int b200_conv2d_tc_supported(int pass, int N, int H, int W, int C, int K, int R,
 int b200_weight_prep(const float* w_krsc, void* w_krsc_bf16, void* w_crsk_bf16, int K, int RS, int C,
                      b200_stream_t stream);
 
+/* The same for n filters in one launch. `table` is a DEVICE array of n 40-byte records
+ * { const float* w_krsc; void* w_krsc_bf16; void* w_crsk_bf16; int32 K, RS, C, pad; }. */
+int b200_weight_prep_multi(const void* table, int n, b200_stream_t stream);
+
 /* ---- convolution (aten::convolution / convolution_backward; call sites residual_block.py:73,78,
  * 81,86,179-203,92,208 and resnet.py:69-75). Shapes: x [N,H,W,C], w [K,R,S,C], y [N,P,Q,K] with
  * P = (H + 2*pad - R)/stride + 1. stride in {1,2}. --------------------------------------------- */

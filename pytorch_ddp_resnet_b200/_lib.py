@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200_device_check": (c_int, []),
     "b200_conv2d_tc_supported": (c_int, [c_int] + _CONV_DIMS),
     "b200_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "b200_weight_prep_multi": (c_int, [_P, c_int, _P]),
     "b200_conv2d_workspace_bytes": (c_size_t, [c_int] + _CONV_DIMS + [c_int]),
     "b200_conv2d_fprop": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
     "b200_conv2d_dgrad": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),

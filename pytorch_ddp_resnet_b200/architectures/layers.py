@@ -113,14 +113,50 @@ class Conv2d(tc.nn.Module):
                 v = self.weight.detach().reshape(self.out_channels, self.in_channels)[:, None, None, :]
         return v.detach()
 
+    def _key(self):
+        w = self.weight
+        return (w.data_ptr(), w._version, _weight_generation[0])
+
     def working_copies(self):
         """(bf16 KRSC, bf16 CRSK), re-made only when the master weight changed."""
-        w = self.weight
-        key = (w.data_ptr(), w._version, _weight_generation[0])
+        key = self._key()
         if self._cache is None or self._cache[0] != key:
             wk, wt = ops.weight_prep(self.krsc().contiguous())
             self._cache = (key, wk, wt)
         return self._cache[1], self._cache[2]
+
+
+class WeightPrepPlan:
+    """Batched filter preparation for a whole model: persistent bf16 KRSC / CRSK buffers for every conv
+    and ONE kernel launch per step that refreshes all stale ones (instead of two launches per conv)."""
+
+    def __init__(self, convs):
+        self.convs = list(convs)
+        self.table = None
+        self.ptrs = None
+
+    def refresh(self):
+        convs = self.convs
+        if not convs or not convs[0].weight.is_cuda:
+            return
+        keys = [c._key() for c in convs]
+        if all(c._cache is not None and c._cache[0] == k for c, k in zip(convs, keys)):
+            return
+        ptrs = tuple(c.weight.data_ptr() for c in convs)
+        if self.table is None or self.ptrs != ptrs:
+            entries = []
+            for c in convs:
+                w = c.krsc().contiguous()
+                K, R, S, C = w.shape
+                wk = torch.empty((K, R, S, C), dtype=torch.bfloat16, device=w.device)
+                wt = torch.empty((C, R, S, K), dtype=torch.bfloat16, device=w.device)
+                entries.append((w, wk, wt))
+            self.entries = entries
+            self.table = ops.weight_prep_table(entries)
+            self.ptrs = ptrs
+        ops.weight_prep_multi(self.table, len(convs))
+        for c, k, (_, wk, wt) in zip(convs, keys, self.entries):
+            c._cache = (k, wk, wt)
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "

@@ -12,7 +12,7 @@ from typing import List, Tuple
 import torch as tc
 
 from pytorch_ddp_resnet_b200.architectures.layers import (
-    Conv2d, BatchNorm2d, ReLU, Linear, AvgPool2d, MaxPool2d, TopConvFn, BnActFn,
+    Conv2d, BatchNorm2d, ReLU, Linear, AvgPool2d, MaxPool2d, TopConvFn, BnActFn, WeightPrepPlan,
 )
 from pytorch_ddp_resnet_b200.architectures.residual_block import (
     ResidualBlock, BottleneckResidualBlock,
@@ -69,6 +69,7 @@ class ResNet(tc.nn.Module):
         self._dropout_prob = dropout_prob
         self._architecture = self._build(tokenize(architecture_spec))
         self._init_weights()
+        self._prep_plan = None
 
     def _stack(self, block_cls, depth: int, width_in: int, downsample: bool) -> tc.nn.Sequential:
         width_out = 2 * width_in if downsample else width_in
@@ -114,6 +115,10 @@ class ResNet(tc.nn.Module):
                     m.weight.copy_(w)
 
     def forward(self, x):
+        if x.is_cuda:  # refresh every stale bf16 filter copy of the model in one launch
+            if self._prep_plan is None:
+                self._prep_plan = WeightPrepPlan(m for m in self.modules() if isinstance(m, Conv2d))
+            self._prep_plan.refresh()
         mods = list(self._architecture)
         i = 0
         while i < len(mods):

@@ -840,6 +840,16 @@ extern "C" int b200_weight_prep(const float* w_krsc, void* w_krsc_bf16, void* w_
   return 0;
 }
 
+extern "C" int b200_weight_prep_multi(const void* table, int n, b200_stream_t stream) {
+  B200_REQUIRE(table && n > 0, "weight_prep_multi: bad arguments");
+  static_assert(sizeof(WeightPrepEntry) == 40, "table layout is part of the ABI: 3 pointers + 4 ints");
+  dim3 grid(num_sms(), n);  // blocks beyond a small tensor's tile count exit at once
+  weight_prep_multi_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
+      reinterpret_cast<const WeightPrepEntry*>(table));
+  B200_LAUNCH_CHECK("weight_prep_multi_kernel");
+  return 0;
+}
+
 extern "C" int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,
                                           b200_stream_t stream) {
   B200_REQUIRE(x && y, "nchw_f32_to_nhwc_bf16: null pointer");

@@ -541,6 +541,45 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, bf16* __res
   }
 }
 
+// All filters of a model in ONE launch: blockIdx.y = tensor, blocks stride over its 32x32 (K x C) tiles
+// per filter tap; every tile is read once (coalesced along C) and written twice: bf16 KRSC (same layout)
+// and bf16 CRSK (transposed through shared memory).
+struct WeightPrepEntry {
+  const float* w;   // fp32 [K][RS][C]
+  bf16* wk;         // bf16 [K][RS][C]
+  bf16* wt;         // bf16 [C][RS][K]
+  int K, RS, C;
+  int pad_;
+};
+
+__global__ void weight_prep_multi_kernel(const WeightPrepEntry* __restrict__ table) {
+  __shared__ float tile[32][33];
+  const WeightPrepEntry e = table[blockIdx.y];
+  const int tk = (e.K + 31) / 32, tc_ = (e.C + 31) / 32;
+  const int ntiles = tk * tc_ * e.RS;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int rs = t / (tk * tc_);
+    const int k0 = ((t / tc_) % tk) * 32, c0 = (t % tc_) * 32;
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, c = c0 + threadIdx.x;
+      float v = 0.f;
+      if (k < e.K && c < e.C) {
+        const size_t o = ((size_t)k * e.RS + rs) * e.C + c;
+        v = e.w[o];
+        e.wk[o] = __float2bfloat16_rn(v);
+      }
+      tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, k = k0 + threadIdx.x;
+      if (k < e.K && c < e.C)
+        e.wt[((size_t)c * e.RS + rs) * e.K + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // im2col for convolutions with very few input channels (the 3-channel stems): col[pix][kk] with
 // kk = (r*S + s)*C + c, zero padded to Kpad columns, so the conv becomes a 1x1 conv over Kpad channels

@@ -79,6 +79,20 @@ def weight_prep(w_krsc_f32: torch.Tensor, want_crsk: bool = True) -> Tuple[torch
     return wk, wt
 
 
+def weight_prep_table(entries) -> torch.Tensor:
+    """Device table for weight_prep_multi from [(w_krsc_f32, wk_bf16, wt_bf16)]: 40-byte records."""
+    import struct
+    blob = b"".join(struct.pack("<QQQiiii", w.data_ptr(), wk.data_ptr(), wt.data_ptr(), w.shape[0],
+                                w.shape[1] * w.shape[2], w.shape[3], 0) for w, wk, wt in entries)
+    host = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    return host.to(entries[0][0].device)
+
+
+def weight_prep_multi(table: torch.Tensor, n: int) -> None:
+    _lib.require_device(table.device.index or 0)
+    _lib.call("b200_weight_prep_multi", table.data_ptr(), n, _stream())
+
+
 def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda and x.dim() == 4
     _lib.require_device(x.device.index or 0)
