@@ -105,10 +105,19 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on the host cores
 # --------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms use every core the process may run on."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_steps(batch: int, steps: int, warmup: int):
     """img/s of the oracle training step (WRN-28-10, fp32, all host threads) on a bounded sample."""
     import torch
     from oracle import resnet_oracle as O
+    use_all_host_threads()
     state = O.init_state(SPEC, PREACT, USE_PROJ, seed=0)
     bufs = {}
     g = torch.Generator().manual_seed(1234)
@@ -128,7 +137,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
+    cores = use_all_host_threads()
     batch = 16
     steps = max(1, min(args.steps, 6))
     warm = max(1, min(args.warmup, 1))
@@ -324,7 +333,7 @@ def run_ours(args):
                      "step_conv_frac_of_sustained": conv_tflops_in_step / pk["bf16_sustained"]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
+        cores = use_all_host_threads()
         ips, _ = cpu_steps(8, 2, 1)
         line["cpu_baseline"] = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
                                 "sample": "2 steps (+1 warm-up) of batch 8 of the same WRN-28-10 workload, "

@@ -92,6 +92,8 @@ class Conv2d(tc.nn.Module):
         else:
             self.register_parameter("bias", None)
         self._cache = None
+        # optional fp32 [K,R,S,C] destination for the weight gradient (a view into a flat all-reduce buffer)
+        self.grad_out = None
 
     def _apply(self, fn, recurse=True):
         # keep the KRSC physical layout across .to()/.cuda()/.float() (1x1 filters are ambiguous)
@@ -271,7 +273,8 @@ class TopConvFn(torch.autograd.Function):
         mod = ctx.mod
         g = grad_nhwc(gy)
         k = mod.kernel_size
-        dw, db = ops.conv_wgrad(g, xh, k, k, mod.stride, mod.padding, want_dbias=mod.bias is not None)
+        dw, db = ops.conv_wgrad(g, xh, k, k, mod.stride, mod.padding, want_dbias=mod.bias is not None,
+                                out=mod.grad_out)
         dx = None
         if ctx.need_dx:
             d = ops.conv_dgrad(g, wt, (xh.shape[1], xh.shape[2]), mod.stride, mod.padding)

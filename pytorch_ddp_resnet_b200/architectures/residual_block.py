@@ -126,7 +126,8 @@ class _BlockFn(torch.autograd.Function):
             for j in range(n - 1, -1, -1):
                 c = convs[j]
                 a, hin, st = ctx.saved_act[j], ctx.saved_in[j], ctx.stats[j]
-                dw, _ = ops.conv_wgrad(cur, a, c.kernel_size, c.kernel_size, c.stride, c.padding)
+                dw, _ = ops.conv_wgrad(cur, a, c.kernel_size, c.kernel_size, c.stride, c.padding,
+                                       out=c.grad_out)
                 dws[j] = dw
                 da = ops.conv_dgrad(cur, ctx.wt[j], (a.shape[1], a.shape[2]), c.stride, c.padding)
                 addend = dskip if (j == 0 and identity) else None
@@ -143,7 +144,8 @@ class _BlockFn(torch.autograd.Function):
             for j in range(n - 1, -1, -1):
                 c = convs[j]
                 d = ctx.saved_act[j]
-                dw, _ = ops.conv_wgrad(cur, d, c.kernel_size, c.kernel_size, c.stride, c.padding)
+                dw, _ = ops.conv_wgrad(cur, d, c.kernel_size, c.kernel_size, c.stride, c.padding,
+                                       out=c.grad_out)
                 dws[j] = dw
                 fuse_skip = (j == 0 and identity and p == 0.0)
                 dd = ops.conv_dgrad(cur, ctx.wt[j], (d.shape[1], d.shape[2]), c.stride, c.padding,
@@ -162,7 +164,7 @@ class _BlockFn(torch.autograd.Function):
 
         dproj = None
         if has_proj:
-            dproj, _ = ops.conv_wgrad(dskip, ctx.xsub, 1, 1, 1, 0)
+            dproj, _ = ops.conv_wgrad(dskip, ctx.xsub, 1, 1, 1, 0, out=block._proj.grad_out)
             dxs = ops.conv_dgrad(dskip, ctx.pt, (ctx.xsub.shape[1], ctx.xsub.shape[2]), 1, 0)
             ops.upsample_add_(dx, dxs)
         elif block._downsample:

@@ -146,14 +146,20 @@ def conv_dgrad(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, addend
     return dx
 
 
-def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = False, algo=None):
-    """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None)."""
+def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = False, algo=None,
+               out=None):
+    """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None). `out`: optional preallocated dw (e.g. a view
+    into a flat gradient buffer that a single NCCL all-reduce covers)."""
     _check_act(dy, "conv_wgrad.dy")
     _check_act(x, "conv_wgrad.x")
     N, H, W, C = x.shape
     Nd, P, Q, K = dy.shape
     assert Nd == N and _out_hw(H, W, R, S, stride, pad) == (P, Q)
-    dw = torch.empty((K, R, S, C), dtype=torch.float32, device=x.device)
+    if out is not None:
+        assert out.shape == (K, R, S, C) and out.dtype == torch.float32 and out.is_contiguous()
+        dw = out
+    else:
+        dw = torch.empty((K, R, S, C), dtype=torch.float32, device=x.device)
     db = torch.empty((K,), dtype=torch.float32, device=x.device) if want_dbias else None
     algo = conv_algo() if algo is None else algo
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_WGRAD, N, H, W, C, K, R, S, stride, pad, algo)
