@@ -285,16 +285,24 @@ struct BnActBwdArgs {
   const uint64_t* seed_offset;
 };
 
-// g = dy masked by relu (y != 0) and dropout (regenerated from the counter RNG), scaled by 1/(1-p)
+// g = dy * mask / (1-p). With a fused ReLU the saved forward output y is non-zero exactly where the unit
+// was both active and kept, so (y != 0) is the combined ReLU + dropout mask and no random numbers are
+// regenerated; without ReLU the dropout mask is regenerated from the counter RNG.
 __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t seed, size_t v,
                                                  const Vec8& dv, const Vec8& yv, float* g) {
   dv.to_float(g);
-  if (a.drop_thr) dropout8<true>(g, seed, v, a.drop_thr, a.inv_keep);
   if (a.relu) {
     float yf[8];
     yv.to_float(yf);
+    if (a.drop_thr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = (yf[j] != 0.f) ? g[j] : 0.f;
+      for (int j = 0; j < 8; ++j) g[j] = (yf[j] != 0.f) ? round_bf16(g[j] * a.inv_keep) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = (yf[j] != 0.f) ? g[j] : 0.f;
+    }
+  } else if (a.drop_thr) {
+    dropout8<true>(g, seed, v, a.drop_thr, a.inv_keep);
   }
 }
 
