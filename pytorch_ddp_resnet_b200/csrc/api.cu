@@ -767,9 +767,10 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
   const size_t npix = (size_t)N * P * Q;
   if (dbias) {
     B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
-    const int ppc = 512;
-    conv_dbias_kernel<<<(unsigned)((npix + ppc - 1) / ppc), 256, 0, st>>>((const bf16*)dy, dbias, npix,
-                                                                          K, ppc);
+    B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
+    const int ppc = (int)std::max<size_t>(64, (npix + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4));
+    conv_dbias_kernel<<<dim3((unsigned)((npix + ppc - 1) / ppc), 1), 256, 0, st>>>((const bf16*)dy, dbias,
+                                                                                    npix, K, ppc);
     B200_LAUNCH_CHECK("conv_dbias_kernel");
   }
   const bool tc = use_tc(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);

@@ -127,15 +127,41 @@ __global__ void conv_wgrad_direct_kernel(const bf16* __restrict__ dy, const bf16
   else atomicAdd(dw + idx, acc);
 }
 
-// dbias[k] = sum over pixels of dy[pix][k]; block per chunk of pixels, thread per k (strided)
+// dbias[k] = sum over pixels of dy[pix][k]: block = (8-channel group lanes) x (pixel lanes) over a chunk
+// of pixels, 16-byte loads, shared-memory reduction over the pixel lanes, one atomic per channel per block
 __global__ void conv_dbias_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias,
                                   size_t npix, int K, int pix_per_chunk) {
+  __shared__ float red[256 * 8];
+  const int CG = K / 8;
+  const int CGb = min(256, CG);
+  const int RP = 256 / CGb;
+  const int cg = threadIdx.x % CGb, rl = threadIdx.x / CGb;
   const size_t p0 = (size_t)blockIdx.x * pix_per_chunk;
   const size_t p1 = min(npix, p0 + (size_t)pix_per_chunk);
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float acc = 0.f;
-    for (size_t pix = p0; pix < p1; ++pix) acc += __bfloat162float(dy[pix * K + k]);
-    atomicAdd(dbias + k, acc);
+  for (int cgb = blockIdx.y * CGb; cgb < CG; cgb += gridDim.y * CGb) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int cgi = cgb + cg;
+    if (rl < RP && cgi < CG) {
+      for (size_t pix = p0 + rl; pix < p1; pix += RP) {
+        Vec8 v;
+        v.raw = ldg_stream(dy + pix * K + (size_t)cgi * 8);
+        float f[8];
+        v.to_float(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if (rl == 0 && cgi < CG) {
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+        for (int r = 0; r < RP; ++r) s += red[(r * CGb + cg) * 8 + j];
+        atomicAdd(dbias + cgi * 8 + j, s);
+      }
+    }
+    __syncthreads();
   }
 }
 

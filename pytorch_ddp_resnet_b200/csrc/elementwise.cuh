@@ -595,25 +595,34 @@ __global__ void weight_prep_multi_kernel(const WeightPrepEntry* __restrict__ tab
 // -------------------------------------------------------------------------------------------------
 __global__ void im2col_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W,
                               int C, int R, int S, int stride, int pad, int P, int Q, int Kpad) {
-  const size_t total = (size_t)N * P * Q * Kpad;
+  // one thread per (pixel, 8-column group): 16-byte stores, the (r, s, c) walk advances incrementally
+  const int groups = Kpad / 8;
+  const size_t total = (size_t)N * P * Q * groups;
   const int rsc = R * S * C;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(idx % Kpad);
-    const size_t pix = idx / Kpad;
-    float v = 0.f;
-    if (kk < rsc) {
-      const int c = kk % C;
-      const int s = (kk / C) % S;
-      const int r = kk / (C * S);
-      const int q = (int)(pix % Q);
-      const int p = (int)((pix / Q) % P);
-      const int n = (int)(pix / ((size_t)Q * P));
-      const int ih = p * stride + r - pad, iw = q * stride + s - pad;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-        v = __bfloat162float(x[(((size_t)n * H + ih) * W + iw) * C + c]);
+    const int gi = (int)(idx % groups);
+    const size_t pix = idx / groups;
+    const int q = (int)(pix % Q);
+    const int p = (int)((pix / Q) % P);
+    const int n = (int)(pix / ((size_t)Q * P));
+    int kk = gi * 8;
+    int c = kk % C, s = (kk / C) % S, r = kk / (C * S);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j, ++kk) {
+      float v = 0.f;
+      if (kk < rsc) {
+        const int ih = p * stride + r - pad, iw = q * stride + s - pad;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          v = __bfloat162float(x[(((size_t)n * H + ih) * W + iw) * C + c]);
+      }
+      f[j] = v;
+      if (++c == C) { c = 0; if (++s == S) { s = 0; ++r; } }
     }
-    col[idx] = __float2bfloat16_rn(v);
+    Vec8 o;
+    o.from_float(f);
+    *reinterpret_cast<uint4*>(col + pix * Kpad + (size_t)gi * 8) = o.raw;
   }
 }
 

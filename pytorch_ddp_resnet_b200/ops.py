@@ -152,6 +152,17 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
     into a flat gradient buffer that a single NCCL all-reduce covers)."""
     _check_act(dy, "conv_wgrad.dy")
     _check_act(x, "conv_wgrad.x")
+    if _overlap["on"]:
+        side = _wgrad_side_stream(x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        _overlap["on"] = False
+        try:
+            with torch.cuda.stream(side):
+                res = conv_wgrad(dy, x, R, S, stride, pad, want_dbias, algo, out)
+        finally:
+            _overlap["on"] = True
+        _overlap["keep"][x.device.index].append((dy, x, res))
+        return res
     N, H, W, C = x.shape
     Nd, P, Q, K = dy.shape
     assert Nd == N and _out_hw(H, W, R, S, stride, pad) == (P, Q)
@@ -167,6 +178,45 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
     _lib.call("b200_conv2d_wgrad", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _p(db),
               N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
     return dw, db
+
+
+# ---- optional overlap of wgrad with the rest of backward ------------------------------------------
+# Weight gradients are not consumed until the optimizer step, so inside `wgrad_overlap(device)` every
+# conv_wgrad is enqueued on a side stream (forked from the current stream at its point of issue) and runs
+# concurrently with the dgrad / BN-backward chain; `join_wgrad(device)` re-joins the streams. Tensors that
+# cross streams are kept alive until the join (no allocator reuse hazard, also under graph capture).
+_overlap = {"on": False, "side": {}, "keep": {}}
+
+
+class wgrad_overlap:
+    def __init__(self, device: torch.device, enabled: bool = True):
+        self.device, self.enabled = device, enabled
+
+    def __enter__(self):
+        self.prev = _overlap["on"]
+        _overlap["on"] = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _overlap["on"] = self.prev
+        join_wgrad(self.device)
+        return False
+
+
+def join_wgrad(device: torch.device) -> None:
+    side = _overlap["side"].get(device.index)
+    if side is not None and _overlap["keep"].get(device.index):
+        torch.cuda.current_stream(device).wait_stream(side)
+        _overlap["keep"][device.index] = []
+
+
+def _wgrad_side_stream(device: torch.device):
+    side = _overlap["side"].get(device.index)
+    if side is None:
+        side = torch.cuda.Stream(device=device)
+        _overlap["side"][device.index] = side
+        _overlap["keep"][device.index] = []
+    return side
 
 
 def conv_tc_supported(pass_: int, N, H, W, C, K, R, S, stride, pad) -> bool:

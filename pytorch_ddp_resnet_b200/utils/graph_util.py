@@ -115,8 +115,11 @@ class GraphedTrainStep:
 
     @staticmethod
     def _forward_backward(module, x, y) -> Dict[str, torch.Tensor]:
+        import os
         m = compute_losses_and_metrics(logits=module(x), labels=y)
-        m["loss"].backward()
+        # wgrad kernels run on a side stream, concurrently with the dgrad / BN-backward chain
+        with ops.wgrad_overlap(x.device, enabled=os.environ.get("B200_WGRAD_OVERLAP", "1") != "0"):
+            m["loss"].backward()
         return {k: v.detach() for k, v in m.items()}
 
     def _exchange(self) -> None:
