@@ -272,6 +272,78 @@ def test_cuda_graph_step_equals_eager_steps():
     assert len(set(ls)) == 4, ls
 
 
+def test_graphed_step_ragged_batch_falls_back_to_eager():
+    """A batch whose shape differs from the captured one (last batch of an epoch) runs eagerly with the
+    same maths, and the graph keeps working afterwards."""
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
+    from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
+    spec = "c3,16,3,1,1 n a r1 r1 ap16,1,0 fc32,10"
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 3, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 10, (8,), generator=g).cuda()
+    torch.manual_seed(0)
+    m = ResNet(spec, False, True, 0.0).cuda().train()
+    opt = get_optimizer("SGD", m, dict(SGD))
+    step = GraphedTrainStep(m, opt, x, y)
+    l0 = step(x, y)["loss"].item()
+    l_ragged = step(x[:5], y[:5])["loss"].item()       # odd batch: direct/single-CTA kernels, eager path
+    l1 = step(x, y)["loss"].item()
+    assert all(v == v and v < 20 for v in (l0, l_ragged, l1))
+    assert l1 < l0  # still training on the same batch
+
+
+def test_gradscaler_drives_fused_sgd():
+    """The reference's loop steps through GradScaler on CUDA (training.py:99-110). FusedSGD takes the
+    scale / found_inf tensors itself: a scaled step must equal the unscaled one, an inf must skip it."""
+    from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
+    torch.manual_seed(0)
+    w1 = torch.nn.Parameter(torch.randn(64, 33, device="cuda"))
+    w2 = torch.nn.Parameter(w1.detach().clone())
+    o1 = get_optimizer("SGD", torch.nn.ParameterList([w1]), dict(SGD))
+    o2 = get_optimizer("SGD", torch.nn.ParameterList([w2]), dict(SGD))
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    gvals = [torch.randn_like(w1) for _ in range(3)]
+    for gv in gvals:
+        o1.zero_grad(set_to_none=True)
+        o2.zero_grad(set_to_none=True)
+        (w1 * gv).sum().backward()
+        o1.step()
+        scaler.scale((w2 * gv).sum()).backward()
+        scaler.step(o2)
+        scaler.update()
+    assert torch.allclose(w1, w2, atol=1e-6, rtol=1e-5)
+    before = w2.detach().clone()
+    o2.zero_grad(set_to_none=True)
+    scaler.scale((w2 * torch.full_like(w2, float("inf"))).sum()).backward()
+    scaler.step(o2)
+    scaler.update()
+    assert torch.equal(w2.detach(), before)  # step skipped
+    assert scaler.get_scale() < 1024.0       # and the scale backed off
+
+
+@pytest.mark.parametrize("batch", [1, 3, 7])
+def test_odd_batch_sizes_train_and_eval(batch):
+    from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from oracle import resnet_oracle as O
+    spec = "c3,32,3,1,1 r1 r1 n a ap16,1,0 fc64,10"
+    init = O.init_state(spec, True, True, seed=2)
+    m = ResNet(spec, True, True, 0.0)
+    m.load_state_dict(init)
+    m = m.cuda().train()
+    g = torch.Generator().manual_seed(batch)
+    x = torch.randn(batch, 3, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 10, (batch,), generator=g).cuda()
+    logits = m(x)
+    compute_losses_and_metrics(logits=logits, labels=y)["loss"].backward()
+    state = {k: v.clone().cuda() for k, v in init.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = O.forward(state, x, spec, True, True, 0.0, training=True)
+    assert rel_l2(logits, ref) < 5e-2
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
 def test_no_silent_fallback_when_library_missing(monkeypatch):
     from pytorch_ddp_resnet_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
