@@ -370,6 +370,76 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
   return 0;
 }
 
+static bool conv_use_halo() {
+  // B200_CONV_HALO=0 disables the halo-reuse kernel (3x3 / stride 1 / pad 1 layers fall back to conv_tc2)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_CONV_HALO");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
+// make_tmap_nhwc with an explicit box (the halo patch is wider / taller than the output tile)
+template <int KC>
+static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
+                            int wcols, const TapTable& taps, void* out, const void* residual,
+                            const float* bias, int Nimg, int P, int Q, int BN, cudaStream_t st) {
+  static bool attr_set = false;
+  const int max_dyn = 228352;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_dyn));
+    attr_set = true;
+  }
+  ConvHaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tiles_w = Q / 8; a.tiles_h = P / 16;
+  a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = Cin / KC;
+  a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
+  a.num_tiles = a.tiles_w * a.tiles_h * Nimg * a.n_ntiles;
+  a.ntaps = taps.n;
+  a.patch_bytes = (uint32_t)HALO_PW * HALO_PH * KC * 2u;
+  a.btile_bytes = (((uint32_t)(BN / 2) * KC * 2u) + 1023u) & ~1023u;
+  const int budget = max_dyn - 1024 - 2 * (int)a.patch_bytes;
+  // taps per filter stage: all 9 when three such stages fit (>= 18 MMAs per barrier round trip), else 3
+  a.tpb = (budget / (int)(taps.n * a.btile_bytes) >= 3) ? taps.n : 3;
+  if (const char* e = getenv("B200_HALO_TPB")) a.tpb = std::max(1, std::min(atoi(e), taps.n));
+  a.ntg = (taps.n + a.tpb - 1) / a.tpb;
+  a.bstage_bytes = (uint32_t)a.tpb * a.btile_bytes;
+  a.bstages = std::min(HALO_BSTAGES_MAX, budget / (int)a.bstage_bytes);
+  B200_REQUIRE(a.bstages >= 2, "conv_tc2h: filter ring does not fit in shared memory");
+  for (int t = 0; t < taps.n; ++t) {
+    a.tap_rowoff[t] = (taps.dh[t] + 1) * HALO_PW + (taps.dw[t] + 1);
+    a.tap_wcol[t] = taps.wcol[t];
+  }
+  a.out = reinterpret_cast<bf16*>(out);
+  a.residual = reinterpret_cast<const bf16*>(residual);
+  a.bias = bias;
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, HALO_PW, HALO_PH, 1)) return rc;
+  if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
+  size_t dyn = 2 * (size_t)a.patch_bytes + (size_t)a.bstages * a.bstage_bytes + 1024;
+  dyn = std::max<size_t>(dyn, 120 * 1024);
+  const int num_ptiles = a.num_tiles / 2;
+  const int grid = std::min(num_ptiles, num_sms() / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC>, tmA, tmB, a));
+  B200_LAUNCH_CHECK("conv_tc2h_kernel");
+  return 0;
+}
+
 static bool conv_use_pair() {
   // B200_CONV_PAIR=0 disables the cta_group::2 kernel (falls back to the single-CTA kernel)
   static int v = -1;
@@ -407,10 +477,27 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   const bool pair = conv_use_pair() && m_tiles_all % 2 == 0 && BN % 32 == 0;
   // (tried: 64-channel blocks with a partial last block per tap for Cin = 160 - the extra predicate per
   //  MMA slowed the issue loop more than SWIZZLE_128B gained; KC stays a divisor of Cin)
+  // halo-reuse kernel: 3x3 taps with unit displacements on an un-split input, maps that tile in 8x16
+  {
+    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg;
+    for (int i = 0; unit && i < taps.n; ++i)
+      unit = taps.dn[i] == 0 && taps.dh[i] >= -1 && taps.dh[i] <= 1 && taps.dw[i] >= -1 && taps.dw[i] <= 1;
+    const int mt8x16 = (Q / 8) * (P / 16) * Nimg;
+    if (unit && conv_use_halo() && conv_use_pair() && Q % 8 == 0 && P % 16 == 0 && mt8x16 % 2 == 0 &&
+        BN % 32 == 0 && Cin % KC == 0 && KC >= 32) {
+      if (KC == 64)
+        return launch_conv_tc2h<64>(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias,
+                                    Nimg, P, Q, BN, st);
+      return launch_conv_tc2h<32>(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias,
+                                  Nimg, P, Q, BN, st);
+    }
+  }
   a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = (Cin + KC - 1) / KC; a.cin = Cin;
   a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
   a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles;
   a.taps = taps;
+  if (const char* e = getenv("B200_PROBE_ROWOFF")) a.probe_rowoff = atoi(e);
+  if (const char* e = getenv("B200_PROBE_BASEOFF")) a.probe_baseoff = atoi(e);
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;

@@ -47,6 +47,8 @@ struct ConvTcArgs {
   uint32_t stage_bytes;
   uint32_t a_bytes;                 // 128 * KC * 2
   uint32_t tx_bytes;                // bytes landed per K-block (per CTA)
+  int probe_rowoff;                 // PROBE ONLY: A box loaded `rowoff` pixels early, descriptor starts rowoff rows in
+  int probe_baseoff;                // PROBE ONLY: value of the descriptor's base_offset field
   int gblk;                         // K-blocks per pipeline stage (SM-pair kernel)
   uint32_t block_bytes;             // shared-memory bytes of one K-block (A tile + B tile)
   TapTable taps;
@@ -136,7 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
             uint8_t* b_dst = a_dst + args.a_bytes;
             mbar_expect_tx(&full_bar[s], args.tx_bytes);
-            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw, ch, cn);
+            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw - args.probe_rowoff, ch, cn);
             if (CS == 1) {
               tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
             } else {
@@ -168,11 +170,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
-          const uint32_t alo = smem_desc_lo(a_addr, 16);
+          const uint32_t alo = smem_desc_lo(a_addr + (uint32_t)args.probe_rowoff * KMajorCfg<KC>::ROW_BYTES, 16);
           const uint32_t blo = smem_desc_lo(a_addr + args.a_bytes, 16);
+          const uint32_t ahi = dhi | ((uint32_t)(args.probe_baseoff & 7) << 17);  // base_offset: bits [49,52)
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
-            umma_bf16_ss(d_addr, smem_desc_join(alo + 2 * k, dhi), smem_desc_join(blo + 2 * k, dhi),
+            umma_bf16_ss(d_addr, smem_desc_join(alo + 2 * k, ahi), smem_desc_join(blo + 2 * k, dhi),
                          idesc, (it | k) != 0 ? 1u : 0u);
           }
           if (CS == 1) umma_commit(&empty_bar[s]);
@@ -449,6 +452,241 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *reinterpret_cast<uint4*>(orow + c) = o0.raw;
           *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
         }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv_tc2h_kernel: SM-pair kernel with HALO REUSE for 3x3 / stride 1 / pad 1 convolutions.
+// The output tile is 8 pixels wide x 16 rows, so every 8-row MMA group is one image-row segment and the
+// groups of a shifted window sit at a uniform stride in shared memory. Per K-block ONE activation patch
+// (18 rows x 16 pixels, halo included, zero-filled by TMA outside the image) is staged and all 9 taps read
+// it through descriptor start offsets of (dh+1)*16 + (dw+1) rows (measured on B200: the UMMA swizzle
+// follows absolute shared-memory address bits, so a start address that is not 8-row aligned is legal with
+// base_offset = 0). Activation traffic through TMA drops from 9 x 16 KB to 36 KB per K-block; the per-tap
+// filter tiles stream through their own ring (several taps per stage).
+// -------------------------------------------------------------------------------------------------
+constexpr int HALO_PW = 16;   // patch pitch in pixels (8 + 2 halo, padded to a multiple of 8)
+constexpr int HALO_PH = 18;   // patch rows (16 + 2 halo)
+constexpr int HALO_BSTAGES_MAX = 8;
+
+struct ConvHaloArgs {
+  int tiles_w, tiles_h;             // 8x16 tiles per image
+  int n_ntiles, BN, nkc;
+  int P, Q, Nimg, ldo;
+  int num_tiles;                    // pixel tiles x channel tiles (even count of pixel tiles)
+  int ntaps, tpb, ntg;              // taps, taps per filter stage, filter stages per K-block
+  int bstages;
+  uint32_t patch_bytes, btile_bytes, bstage_bytes;
+  int tap_rowoff[TC_MAX_TAPS];      // (dh + 1) * HALO_PW + (dw + 1)
+  int tap_wcol[TC_MAX_TAPS];
+  bf16* out;
+  const bf16* residual;
+  const float* bias;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvHaloArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t pfull_bar[2], pempty_bar[2];
+  __shared__ uint64_t bfull_bar[HALO_BSTAGES_MAX], bempty_bar[HALO_BSTAGES_MAX];
+  __shared__ uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* bring = smem + 2 * (size_t)args.patch_bytes;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pfull_bar[i], 1);
+      mbar_init(&pempty_bar[i], 1);
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    for (int i = 0; i < args.bstages; ++i) {
+      mbar_init(&bfull_bar[i], 1);
+      mbar_init(&bempty_bar[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(&tmem_base_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int tiles_img = args.tiles_w * args.tiles_h;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_ptiles = args.num_tiles >> 1;
+  const int bhalf = args.BN >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int ps = 0, bs = 0;
+    uint32_t pph = 0, bph = 0;
+    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int w0 = (mt % args.tiles_w) * 8;
+      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * 16;
+      const int n0 = mt / tiles_img;
+      for (int kc = 0; kc < args.nkc; ++kc) {
+        mbar_wait(&pempty_bar[ps], pph ^ 1);
+        if (elect_one()) {
+          const uint32_t pfull_leader = map_to_cta(smem_u32(&pfull_bar[ps]), 0);
+          if (leader) mbar_expect_tx(&pfull_bar[ps], 2u * args.patch_bytes);
+          tma_load_4d_2sm(smem + (size_t)ps * args.patch_bytes, &tmA, pfull_leader, kc * KC, w0 - 1,
+                          h0 - 1, n0);
+        }
+        __syncwarp();
+        if (++ps == 2) { ps = 0; pph ^= 1; }
+        for (int tg = 0; tg < args.ntg; ++tg) {
+          mbar_wait(&bempty_bar[bs], bph ^ 1);
+          if (elect_one()) {
+            const uint32_t bfull_leader = map_to_cta(smem_u32(&bfull_bar[bs]), 0);
+            const int t0 = tg * args.tpb;
+            const int cnt = min(args.tpb, args.ntaps - t0);
+            if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * (uint32_t)cnt * args.btile_bytes);
+            uint8_t* dst = bring + (size_t)bs * args.bstage_bytes;
+            for (int j = 0; j < cnt; ++j)
+              tma_load_2d_2sm(dst + (size_t)j * args.btile_bytes, &tmB, bfull_leader,
+                              args.tap_wcol[t0 + j] + kc * KC, nt * args.BN + crank * bhalf);
+          }
+          __syncwarp();
+          if (++bs == args.bstages) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      const uint32_t idesc = make_idesc_bf16(256, args.BN, 0, 0);
+      const uint32_t bhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
+      const uint32_t ahi = smem_desc_hi(HALO_PW * KMajorCfg<KC>::ROW_BYTES, KMajorCfg<KC>::LAYOUT);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t bring_base = smem_u32(bring);
+      const uint32_t bstep = args.btile_bytes >> 4;
+      int ps = 0, bs = 0, as = 0;
+      uint32_t pph = 0, bph = 0, aph = 0;
+      for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
+        uint32_t acc = 0;
+        for (int kc = 0; kc < args.nkc; ++kc) {
+          mbar_wait(&pfull_bar[ps], pph);
+          const uint32_t patch_lo = smem_desc_lo(smem_base + (uint32_t)ps * args.patch_bytes, 16);
+          for (int tg = 0; tg < args.ntg; ++tg) {
+            mbar_wait(&bfull_bar[bs], bph);
+            tc_fence_after();
+            if (elect_one()) {
+              const int t0 = tg * args.tpb;
+              const int cnt = min(args.tpb, args.ntaps - t0);
+              uint32_t blo = smem_desc_lo(bring_base + (uint32_t)bs * args.bstage_bytes, 16);
+              for (int j = 0; j < cnt; ++j) {
+                const uint32_t alo =
+                    patch_lo + (((uint32_t)args.tap_rowoff[t0 + j] * KMajorCfg<KC>::ROW_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  umma_bf16_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, ahi),
+                                   smem_desc_join(blo + 2 * k, bhi), idesc, acc);
+                  acc = 1u;
+                }
+                blo += bstep;
+              }
+              umma_commit_2sm_mcast(&bempty_bar[bs], 3);
+              if (tg == args.ntg - 1) {
+                umma_commit_2sm_mcast(&pempty_bar[ps], 3);
+                if (kc == args.nkc - 1) umma_commit_2sm_mcast(&tfull_bar[as], 3);
+              }
+            }
+            __syncwarp();
+            if (++bs == args.bstages) { bs = 0; bph ^= 1; }
+          }
+          if (++ps == 2) { ps = 0; pph ^= 1; }
+        }
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own TMEM, own 8x16 pixel tile) =====================
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const int wi = m & 7;
+    const int hi = m >> 3;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      const int nt = ct % args.n_ntiles;
+      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int w = (mt % args.tiles_w) * 8 + wi;
+      const int h = ((mt / args.tiles_w) % args.tiles_h) * 16 + hi;
+      const int n = mt / tiles_img;
+      const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
+      const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
+      bf16* orow = args.out + off;
+      const bf16* rrow = args.residual ? args.residual + off : nullptr;
+      const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
+      for (int c = 0; c < args.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (brow) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
+        }
+        if (rrow) {
+          Vec8 r0, r1;
+          r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
+          r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
+          float rf[16];
+          r0.to_float(rf);
+          r1.to_float(rf + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+        }
+        Vec8 o0, o1;
+        o0.from_float(f);
+        o1.from_float(f + 8);
+        *reinterpret_cast<uint4*>(orow + c) = o0.raw;
+        *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
       }
       tc_fence_before();
       __syncwarp();
