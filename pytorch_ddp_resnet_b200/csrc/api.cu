@@ -767,10 +767,110 @@ static int launch_wgrad_tc_cs(int cs, int mt, const CUtensorMap& tmX, const CUte
   }
 }
 
+// pixel-range splits: fill whole waves of the SMs (a 2.2-wave grid idles 30 % of the machine)
+static int pick_wgrad_splits(int cols, int num_ptiles) {
+  const int sms = num_sms();
+  int best = 1;
+  double best_score = -1.0;
+  const int max_splits = std::min(num_ptiles, 64);
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const int per = (num_ptiles + sp - 1) / sp;
+    if ((num_ptiles + per - 1) / per != sp) continue;  // would leave empty splits
+    const long total = (long)cols * sp;
+    const long waves = (total + sms - 1) / sms;
+    double eff = (double)total / (double)(waves * sms);
+    if (per < 8) eff *= 0.85;              // short main loops pay prologue / epilogue overhead
+    if (total < sms) eff *= 0.9;
+    const double score = eff - 0.002 * sp;  // fewer atomics when equal
+    if (score > best_score) { best_score = score; best = sp; }
+  }
+  if (const char* e = getenv("B200_WGRAD_SPLITS")) best = std::max(1, std::min(atoi(e), num_ptiles));
+  const int per = (num_ptiles + best - 1) / best;
+  return (num_ptiles + per - 1) / per;
+}
+
+static bool wgrad_use_halo() {
+  // B200_WGRAD_HALO=0 falls back to the one-window-per-slab kernel
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_WGRAD_HALO");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Halo-reuse SM-pair wgrad (3x3, stride 1, pad 1): see wgrad_tc2h_kernel. Returns -1 when the shape is
+// not covered (the caller then uses the general kernel).
+static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, int C, int K,
+                          const TapTable& taps, float* dw, cudaStream_t st) {
+  if (taps.n != 9 || C % 32 != 0 || K % 32 != 0 || Q % 8 != 0) return -1;
+  for (int t = 0; t < 9; ++t)
+    if (taps.dh[t] != t / 3 - 1 || taps.dw[t] != t % 3 - 1 || taps.dn[t] != 0) return -1;
+  int bh, bn;
+  if (P % 16 == 0) { bh = 16; bn = 1; }
+  else if (P < 16 && 16 % P == 0 && N % (16 / P) == 0) { bh = P; bn = 16 / P; }
+  else return -1;
+  const int BN = pick_bn(K, 32, 160);
+  if (BN <= 0) return -1;
+  int pw = 10;
+  if (const char* e = getenv("B200_WGRAD_PW")) pw = std::max(10, std::min(16, atoi(e)));
+  WgradHaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bh = bh; a.bn = bn; a.pw = pw;
+  a.tiles_w = Q / 8; a.tiles_h = P / bh;
+  a.num_ptiles = a.tiles_w * a.tiles_h * (N / bn);
+  a.ncombo = 3 * (C / 32);
+  a.ncols = ((a.ncombo + 3) / 4 + 1) / 2 * 2;
+  a.BN = BN; a.n_ntiles = K / BN;
+  a.nbh = (BN / 2 + 31) / 32;
+  a.ktot = 9 * C;
+  a.box_bytes = (uint32_t)((16 * pw * 64 + 1023) / 1024 * 1024);
+  a.slab_bytes = 128 * 64;
+  a.stage_bytes = 4 * a.box_bytes + (uint32_t)a.nbh * a.slab_bytes;
+  const int max_dyn = 228352;
+  a.stages = std::min<int>(WGH_STAGES_MAX, (max_dyn - 1024) / (int)a.stage_bytes);
+  if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
+  if (a.stages < 2) return -1;
+  a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles);
+  for (int t = 0; t < 9; ++t) a.wcol[t] = taps.wcol[t];
+  a.dw = dw;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(wgrad_tc2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_dyn));
+    attr_set = true;
+  }
+  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
+  CUtensorMap tmX, tmDy;
+  if (int rc = make_tmap_nhwc(&tmX, act, N, P, Q, C, 32, pw, bh, bn)) return rc;
+  if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, 32, 8, bh, bn)) return rc;
+  size_t dyn = (size_t)a.stages * a.stage_bytes + 1024;
+  dyn = std::max<size_t>(dyn, 120 * 1024);  // one CTA per SM (512 TMEM columns each)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(a.ncols * a.n_ntiles, a.splits);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc2h_kernel, tmX, tmDy, a));
+  B200_LAUNCH_CHECK("wgrad_tc2h_kernel");
+  return 0;
+}
+
 // Shifted-window wgrad launch. act: [Nact][Ha][Wa][C] bf16, dy: [N][P][Q][K] bf16,
 // dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
                         int Q, int K, const TapTable& taps, float* dw, cudaStream_t st) {
+  if (wgrad_use_halo() && Nact == N && Ha == P && Wa == Q) {
+    const int rc = run_wgrad_tc2h(act, dy, N, P, Q, C, K, taps, dw, st);
+    if (rc >= 0) return rc;
+  }
   // slab width: 32 channels (64-byte TMA rows, SWIZZLE_64B) or 16; 64-channel slabs (SWIZZLE_128B, with
   // partial last slabs) are implemented and tested but were not faster (round 1), B200_WGRAD_SLAB=64
   int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
@@ -812,27 +912,7 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   a.nb = (BN + SL - 1) / SL;
   a.ktot = taps.n * C;
   const int cols = a.n_mgroups * a.n_ntiles;
-  // pixel-range splits: fill whole waves of the SMs (a 2.2-wave grid idles 30 % of the machine)
-  {
-    const int sms = num_sms();
-    int best = 1;
-    double best_score = -1.0;
-    const int max_splits = std::min(a.num_ptiles, 64);
-    for (int sp = 1; sp <= max_splits; ++sp) {
-      const int per = (a.num_ptiles + sp - 1) / sp;
-      if ((a.num_ptiles + per - 1) / per != sp) continue;  // would leave empty splits
-      const long total = (long)cols * sp;
-      const long waves = (total + sms - 1) / sms;
-      double eff = (double)total / (double)(waves * sms);
-      if (per < 8) eff *= 0.85;              // short main loops pay prologue / epilogue overhead
-      if (total < sms) eff *= 0.9;
-      const double score = eff - 0.002 * sp;  // fewer atomics when equal
-      if (score > best_score) { best_score = score; best = sp; }
-    }
-    if (const char* e = getenv("B200_WGRAD_SPLITS")) best = std::max(1, std::min(atoi(e), a.num_ptiles));
-    const int per = (a.num_ptiles + best - 1) / best;
-    a.splits = (a.num_ptiles + per - 1) / per;
-  }
+  a.splits = pick_wgrad_splits(cols, a.num_ptiles);
   a.taps = taps;
   a.dw = dw;
   if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));

@@ -945,4 +945,203 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// wgrad_tc2h_kernel: SM-pair wgrad with HALO REUSE for 3x3 / stride 1 / pad 1 filters.
+//
+// The plain wgrad kernel above fetches one 128-pixel x window per (tap, 32-channel chunk) slab, i.e.
+// every activation byte nine times, and is bound by the L2->SM (TMA) path (ncu: ~81 B/clk/SM asked,
+// ~50 delivered). Here one TMA box per (filter row r, chunk) holds the pixel tile widened by the
+// horizontal halo: [bn*bh = 16 pixel rows][PW columns w0-1 ..][32 channels], and the three taps
+// s = 0..2 of that filter row are the SAME box read through descriptors that start s pixel rows (64 B)
+// later (UMMA swizzling follows absolute shared-memory address bits, tools/probe_rowoff.py). The
+// 8-pixel groups of the MMA K dimension are image rows, so their stride (SBO) is PW pixel rows.
+//
+// Work decomposition: a "combo" is (chunk, r); a column is 4 combos = the 4 channel slabs of a
+// 128-row M tile (slab stride LBO = one box); accumulator j of a CTA is filter column s = j of its
+// column, so a CTA owns 3 accumulators of 128 x BN (<= 480 TMEM columns) and issues 24 MMAs per
+// 128-pixel stage from 4 boxes + its half of the dY tile. Two columns form an SM pair
+// (cta_group::2, M = 256): each CTA stages its own boxes and HALF of the dY tile, which halves the dY
+// traffic and the shared-memory read rate per MMA (the limit of the 1-CTA kernel).
+// -------------------------------------------------------------------------------------------------
+constexpr int WGH_STAGES_MAX = 4;
+
+struct WgradHaloArgs {
+  int bh, bn, pw;          // pixel tile = 8 x bh x bn (= 128 pixels); patch width in pixels (>= 10)
+  int tiles_w, tiles_h;
+  int num_ptiles;
+  int ncombo;              // 3 * C / 32
+  int ncols;               // ceil(ncombo / 4) rounded up to even
+  int n_ntiles, BN, nbh;   // Cout tiles; dY slabs per CTA = ceil(BN / 2 / 32)
+  int splits, ktot, stages;
+  uint32_t box_bytes, slab_bytes, stage_bytes;
+  int wcol[TC_MAX_TAPS];
+  float* dw;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc2h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                  const __grid_constant__ WgradHaloArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[WGH_STAGES_MAX];
+  __shared__ uint64_t empty_bar[WGH_STAGES_MAX];
+  __shared__ uint64_t tfull_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tfull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(&tmem_base_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int col = blockIdx.x % args.ncols;   // ncols is even: a cluster is columns (2p, 2p + 1)
+  const int nt = blockIdx.x / args.ncols;
+  const int per = (args.num_ptiles + args.splits - 1) / args.splits;
+  const int pt0 = blockIdx.y * per;
+  const int pt1 = min(args.num_ptiles, pt0 + per);
+  const int q0 = col * 4;
+  const int nbox = max(0, min(4, args.ncombo - q0));
+  const int nbox_peer = max(0, min(4, args.ncombo - (col ^ 1) * 4));
+  const uint32_t b_off = 4u * args.box_bytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t tx = (uint32_t)(nbox + nbox_peer) * args.box_bytes + 2u * (uint32_t)args.nbh * args.slab_bytes;
+    int bc[4], bdh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = min(q0 + i, args.ncombo - 1);
+      bc[i] = (q / 3) * 32;
+      bdh[i] = (q % 3) - 1;
+    }
+    const int bcol0 = nt * args.BN + crank * (args.BN >> 1);
+    const int tiles_hw = args.tiles_w * args.tiles_h;
+    int tw = pt0 % args.tiles_w;
+    int th = (pt0 / args.tiles_w) % args.tiles_h;
+    int tn = pt0 / tiles_hw;
+    for (int pt = pt0; pt < pt1; ++pt) {
+      const int w0 = tw * 8, h0 = th * args.bh, n0 = tn * args.bn;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
+        const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[s]), 0);
+        if (leader) mbar_expect_tx(&full_bar[s], tx);
+        uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
+        uint8_t* b_dst = a_dst + b_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < nbox)
+            tma_load_4d_2sm(a_dst + (size_t)i * args.box_bytes, &tmX, full_leader, bc[i], w0 - 1,
+                            h0 + bdh[i], n0);
+        }
+        for (int i = 0; i < args.nbh; ++i)
+          tma_load_4d_2sm(b_dst + (size_t)i * args.slab_bytes, &tmDy, full_leader, bcol0 + i * 32, w0,
+                          h0, n0);
+      }
+      __syncwarp();
+      if (++s == args.stages) { s = 0; ph ^= 1; }
+      if (++tw == args.tiles_w) {
+        tw = 0;
+        if (++th == args.tiles_h) { th = 0; ++tn; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      const uint32_t idesc = make_idesc_bf16(256, args.BN, 1, 1);
+      const uint32_t ahi = smem_desc_hi((uint32_t)args.pw * 64u, 4u);   // next image row of the patch
+      const uint32_t bhi = smem_desc_hi(8u * 64u, 4u);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t a_kstep = ((uint32_t)args.pw * 128u) >> 4;         // two image rows per K = 16
+      const uint32_t b_kstep = (16u * 64u) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
+          const uint32_t alo = smem_desc_lo(a_addr, args.box_bytes);
+          const uint32_t blo = smem_desc_lo(a_addr + b_off, args.slab_bytes);
+          const uint32_t acc = pt > pt0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t bd = smem_desc_join(blo + k * b_kstep, bhi);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              umma_bf16_ss_2sm(tmem_base + (uint32_t)(j * args.BN),
+                               smem_desc_join(alo + 4u * j + k * a_kstep, ahi), bd, idesc,
+                               (acc | (uint32_t)k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_2sm_mcast(&empty_bar[s], 3);
+          if (pt == pt1 - 1) umma_commit_2sm_mcast(&tfull_bar, 3);
+        }
+        __syncwarp();
+        if (++s == args.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (pt1 > pt0) {
+    // ===================== epilogue (both CTAs): warp quadrant wq = slab = combo q0 + wq ============
+    const int wq = warp & 3;
+    if (wq < nbox) {
+      const int q = q0 + wq;
+      const int c = (q / 3) * 32 + lane;
+      const int r = q % 3;
+      mbar_wait(&tfull_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        float* drow = args.dw + (size_t)nt * args.BN * args.ktot + args.wcol[r * 3 + j] + c;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * args.BN);
+        for (int cc = 0; cc < args.BN; cc += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + cc, v);
+          tmem_ld_wait();
+          if (args.splits == 1) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              drow[(size_t)(cc + jj) * args.ktot] = __uint_as_float(v[jj]);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              atomicAdd(drow + (size_t)(cc + jj) * args.ktot, __uint_as_float(v[jj]));
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+
 }  // namespace b200
