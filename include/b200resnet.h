@@ -93,6 +93,10 @@ int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int
 
 /* ---- batch norm + activation + dropout + skip (aten::native_batch_norm, relu, native_dropout, add,
  * constant_pad_nd, avg_pool2d(k=1,s=2); residual_block.py:58-65,69-98,175-214; resnet.py:111-115) -- */
+/* Size of the ACCUMULATOR workspace of b200_bn_stats / b200_bn_act_bwd: fp64 [2][C] sums + a ticket
+ * counter. Contract: 8-byte aligned, zero-filled before its first use, not shared between streams that
+ * run concurrently; every call leaves it zero-filled again (the block that finishes last folds the sums
+ * into the outputs and clears them), so one cudaMemset when it is allocated is all a caller needs. */
 size_t b200_bn_workspace_bytes(int64_t rows, int C);
 
 /* Per-channel batch statistics of x [rows, C] (bf16): mean, invstd = rsqrt(biased var + eps).

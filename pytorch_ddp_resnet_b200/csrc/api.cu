@@ -54,6 +54,21 @@ static std::atomic<long long> g_launches{0};
 
 static inline cudaStream_t as_stream(b200_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Plain kernel launch through cudaLaunchKernelEx (one code path for ordinary and cluster launches).
+// Programmatic dependent launch was tried here in round 1 (attribute on every launch, griddepcontrol
+// wait at the top of every kernel): no gain on back-to-back kernels inside a CUDA graph and the full
+// training graph hung, so it was removed.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -562,11 +577,9 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
     B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 2, "conv2d_fprop: workspace too small");
     bf16* col = reinterpret_cast<bf16*>(ws);
     bf16* wpad = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(ws) + col_bytes);
-    im2col_kernel<<<ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st>>>(
-        (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
+    launch_k(im2col_kernel, ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st, (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
     B200_LAUNCH_CHECK("im2col_kernel");
-    repitch_rows_kernel<bf16><<<ew_grid((size_t)K * kpad), EW_THREADS, 0, st>>>(
-        (const bf16*)w_krsc, wpad, K, R * S * C, kpad);
+    launch_k(repitch_rows_kernel<bf16>, ew_grid((size_t)K * kpad), EW_THREADS, 0, st, (const bf16*)w_krsc, wpad, K, R * S * C, kpad);
     B200_LAUNCH_CHECK("repitch_rows_kernel");
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
@@ -577,8 +590,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
     const size_t total = (size_t)N * P * Q * K;
-    conv_fprop_direct_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(
-        (const bf16*)x, (const bf16*)w_krsc, bias, (const bf16*)residual, (bf16*)y, d);
+    launch_k(conv_fprop_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)x, (const bf16*)w_krsc, bias, (const bf16*)residual, (bf16*)y, d);
     B200_LAUNCH_CHECK("conv_fprop_direct_kernel");
     return 0;
   }
@@ -588,8 +600,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
     const size_t need = (size_t)N * H * W * C * 2;
     B200_REQUIRE(ws && ws_bytes >= need, "conv2d_fprop: workspace too small (%zu < %zu)", ws_bytes,
                  need);
-    parity_kernel<false><<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
-        (const bf16*)x, (bf16*)ws, N, H, W, C);
+    launch_k(parity_kernel<false>, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)x, (bf16*)ws, N, H, W, C);
     B200_LAUNCH_CHECK("parity_kernel<split>");
     act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
   }
@@ -640,8 +651,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
     const size_t total = (size_t)N * H * W * C;
-    conv_dgrad_direct_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(
-        (const bf16*)dy, (const bf16*)w_crsk, (const bf16*)addend, (bf16*)dx, d);
+    launch_k(conv_dgrad_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)dy, (const bf16*)w_crsk, (const bf16*)addend, (bf16*)dx, d);
     B200_LAUNCH_CHECK("conv_dgrad_direct_kernel");
     return 0;
   }
@@ -684,8 +694,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
                                W2, st))
         return rc;
     }
-  parity_merge_add_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
-      (const bf16*)ws, (const bf16*)addend, (bf16*)dx, N, H, W, C);
+  launch_k(parity_merge_add_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)ws, (const bf16*)addend, (bf16*)dx, N, H, W, C);
   B200_LAUNCH_CHECK("parity_merge_add_kernel");
   return 0;
 }
@@ -936,7 +945,7 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
     B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
     const int ppc = (int)std::max<size_t>(64, (npix + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4));
-    conv_dbias_kernel<<<dim3((unsigned)((npix + ppc - 1) / ppc), 1), 256, 0, st>>>((const bf16*)dy, dbias,
+    launch_k(conv_dbias_kernel, dim3((unsigned)((npix + ppc - 1) / ppc), 1), 256, 0, st, (const bf16*)dy, dbias,
                                                                                     npix, K, ppc);
     B200_LAUNCH_CHECK("conv_dbias_kernel");
   }
@@ -947,15 +956,13 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 4, "conv2d_wgrad: workspace too small");
     bf16* col = reinterpret_cast<bf16*>(ws);
     float* dwpad = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + col_bytes);
-    im2col_kernel<<<ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st>>>(
-        (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
+    launch_k(im2col_kernel, ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st, (const bf16*)x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
     B200_LAUNCH_CHECK("im2col_kernel");
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
     if (int rc = run_wgrad_tc(col, N, P, Q, kpad, dy, N, P, Q, K, tt, dwpad, st)) return rc;
-    repitch_rows_kernel<float><<<ew_grid((size_t)K * R * S * C), EW_THREADS, 0, st>>>(
-        dwpad, dw_krsc, K, kpad, R * S * C);
+    launch_k(repitch_rows_kernel<float>, ew_grid((size_t)K * R * S * C), EW_THREADS, 0, st, dwpad, dw_krsc, K, kpad, R * S * C);
     B200_LAUNCH_CHECK("repitch_rows_kernel");
     return 0;
   }
@@ -968,7 +975,7 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     const int ppc = (int)((npix + chunks - 1) / chunks);
     chunks = (int)((npix + ppc - 1) / ppc);
     if (chunks > 1) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)total * 4, st));
-    conv_wgrad_direct_kernel<<<dim3(bx, chunks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x,
+    launch_k(conv_wgrad_direct_kernel, dim3(bx, chunks), 256, 0, st, (const bf16*)dy, (const bf16*)x,
                                                                dw_krsc, d, ppc);
     B200_LAUNCH_CHECK("conv_wgrad_direct_kernel");
     return 0;
@@ -979,8 +986,7 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     const size_t need = (size_t)N * H * W * C * 2;
     B200_REQUIRE(ws && ws_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)", ws_bytes,
                  need);
-    parity_kernel<false><<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st>>>(
-        (const bf16*)x, (bf16*)ws, N, H, W, C);
+    launch_k(parity_kernel<false>, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)x, (bf16*)ws, N, H, W, C);
     B200_LAUNCH_CHECK("parity_kernel<split>");
     act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
   }
@@ -997,12 +1003,12 @@ extern "C" int b200_weight_prep(const float* w_krsc, void* w_krsc_bf16, void* w_
   cudaStream_t st = as_stream(stream);
   const size_t n = (size_t)K * RS * C;
   if (w_krsc_bf16) {
-    weight_cast_kernel<<<ew_grid(n), EW_THREADS, 0, st>>>(w_krsc, (bf16*)w_krsc_bf16, n);
+    launch_k(weight_cast_kernel, ew_grid(n), EW_THREADS, 0, st, w_krsc, (bf16*)w_krsc_bf16, n);
     B200_LAUNCH_CHECK("weight_cast_kernel");
   }
   if (w_crsk_bf16) {
     dim3 grid((C + 31) / 32, (K + 31) / 32, RS);
-    weight_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(w_krsc, (bf16*)w_crsk_bf16, K, RS, C);
+    launch_k(weight_transpose_kernel, grid, dim3(32, 8), 0, st, w_krsc, (bf16*)w_crsk_bf16, K, RS, C);
     B200_LAUNCH_CHECK("weight_transpose_kernel");
   }
   return 0;
@@ -1012,8 +1018,7 @@ extern "C" int b200_weight_prep_multi(const void* table, int n, b200_stream_t st
   B200_REQUIRE(table && n > 0, "weight_prep_multi: bad arguments");
   static_assert(sizeof(WeightPrepEntry) == 40, "table layout is part of the ABI: 3 pointers + 4 ints");
   dim3 grid(num_sms(), n);  // blocks beyond a small tensor's tile count exit at once
-  weight_prep_multi_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(
-      reinterpret_cast<const WeightPrepEntry*>(table));
+  launch_k(weight_prep_multi_kernel, grid, dim3(32, 8), 0, as_stream(stream), reinterpret_cast<const WeightPrepEntry*>(table));
   B200_LAUNCH_CHECK("weight_prep_multi_kernel");
   return 0;
 }
@@ -1021,8 +1026,7 @@ extern "C" int b200_weight_prep_multi(const void* table, int n, b200_stream_t st
 extern "C" int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,
                                           b200_stream_t stream) {
   B200_REQUIRE(x && y, "nchw_f32_to_nhwc_bf16: null pointer");
-  nchw_f32_to_nhwc_bf16_kernel<<<ew_grid((size_t)N * H * W), EW_THREADS, 0, as_stream(stream)>>>(
-      x, (bf16*)y, N, C, H, W);
+  launch_k(nchw_f32_to_nhwc_bf16_kernel, ew_grid((size_t)N * H * W), EW_THREADS, 0, as_stream(stream), x, (bf16*)y, N, C, H, W);
   B200_LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
   return 0;
 }
@@ -1030,18 +1034,29 @@ extern "C" int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C,
 // -------------------------------------------------------------------------------------------------
 // batch norm family
 // -------------------------------------------------------------------------------------------------
-static int bn_blocks(int64_t rows, int C) {
+// Grids of the HBM-bound BN kernels are ONE wave of resident blocks (measured: 1776 short blocks reach
+// 4.0 TB/s on the 42 MB tensors, 592 long-lived ones with 4 loads in flight per thread 5.3 TB/s).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// One wave of at most num_sms * blocks_per_sm blocks in which every thread walks the same whole number
+// of `unroll`-row batches (a ragged last batch is a full extra memory round trip for the whole grid).
+static int bn_blocks(int64_t rows, int C, int blocks_per_sm, int unroll) {
   const int CG = C / 8;
   const int CGb = std::min(EW_THREADS, CG);
   const int RP = EW_THREADS / CGb;
-  int64_t b = (rows + (int64_t)RP * 8 - 1) / ((int64_t)RP * 8);
-  b = std::min<int64_t>(b, std::min(BN_MAX_BLOCKS, num_sms() * 2));
-  return (int)std::max<int64_t>(1, b);
+  const int64_t batches = (rows + (int64_t)RP * unroll - 1) / ((int64_t)RP * unroll);  // block-batches
+  const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  const int64_t per_block = (batches + cap - 1) / cap;
+  return (int)std::max<int64_t>(1, (batches + per_block - 1) / per_block);
 }
 
+// BN_SLOTS copies of the fp64 accumulators [2][C] + the ticket counter of the last-block finalize
 extern "C" size_t b200_bn_workspace_bytes(int64_t rows, int C) {
   (void)rows;
-  return (size_t)BN_MAX_BLOCKS * 2 * C * sizeof(float);
+  return (size_t)BN_SLOTS * bn_slot_stride(C) * sizeof(double) + 16;
 }
 
 extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum,
@@ -1051,17 +1066,18 @@ extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, floa
   B200_REQUIRE(x && mean && invstd && ws, "bn_stats: null pointer");
   B200_REQUIRE(C % 8 == 0, "bn_stats: C=%d must be a multiple of 8", C);
   B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_stats: workspace too small");
-  cudaStream_t st = as_stream(stream);
-  const int nblk = bn_blocks(rows, C);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_stats: workspace must be 8-byte aligned");
+  static const int bps = std::max(1, env_int("B200_BN_STATS_BPS", 4));
+  BnStatsArgs a;
+  a.x = (const bf16*)x; a.rows = rows; a.C = C; a.eps = eps; a.momentum = momentum;
+  a.mean = mean; a.invstd = invstd; a.running_mean = running_mean; a.running_var = running_var;
+  a.num_batches_tracked = num_batches_tracked;
+  a.accum = reinterpret_cast<double*>(ws);
+  a.ticket = reinterpret_cast<unsigned int*>(a.accum + BN_SLOTS * bn_slot_stride(C));
   const int CG = C / 8;
-  dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
-  bn_stats_partial_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(
-      (const bf16*)x, rows, C, (float*)ws);
-  B200_LAUNCH_CHECK("bn_stats_partial_kernel");
-  bn_stats_finalize_kernel<<<(C + FIN_CH_PER_BLOCK - 1) / FIN_CH_PER_BLOCK, FIN_THREADS, 0, st>>>((const float*)ws, nblk, rows, C, eps,
-                                                            momentum, mean, invstd, running_mean,
-                                                            running_var, num_batches_tracked);
-  B200_LAUNCH_CHECK("bn_stats_finalize_kernel");
+  dim3 grid(bn_blocks(rows, C, bps, 8), (CG + EW_THREADS - 1) / EW_THREADS);
+  launch_k(bn_stats_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), as_stream(stream), a);
+  B200_LAUNCH_CHECK("bn_stats_kernel");
   return 0;
 }
 
@@ -1097,13 +1113,16 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   a.seed_offset = seed_offset;
   {
     const int CG = C / 8;
-    const int CGb = std::min(EW_THREADS, CG);
-    const int RP = EW_THREADS / CGb;
     const int64_t rows = (int64_t)N * H * W;
-    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 2 - 1) / ((int64_t)RP * 2),
-                                                          (int64_t)num_sms() * 12));
-    dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
-    bn_act_fwd_kernel<<<grid, EW_THREADS, 0, as_stream(stream)>>>(a);
+    static const int bps = std::max(1, env_int("B200_BN_FWD_BPS", 4));
+    cudaStream_t fst = as_stream(stream);
+    if (a.skip_mode != 0) {
+      dim3 grid(bn_blocks(rows, C, std::min(bps, 3), 2), (CG + EW_THREADS - 1) / EW_THREADS);
+      launch_k(bn_act_fwd_kernel<2, 3, true>, grid, EW_THREADS, 0, fst, a);
+    } else {
+      dim3 grid(bn_blocks(rows, C, bps, 4), (CG + EW_THREADS - 1) / EW_THREADS);
+      launch_k(bn_act_fwd_kernel<4, 4, false>, grid, EW_THREADS, 0, fst, a);
+    }
   }
   B200_LAUNCH_CHECK("bn_act_fwd_kernel");
   return 0;
@@ -1131,22 +1150,19 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
   if (a.affine) {
     B200_REQUIRE(x && dgamma && dbeta && ws, "bn_act_bwd: null pointer (affine path)");
     B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_act_bwd: workspace too small");
-    const int nblk = bn_blocks(rows, C);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_act_bwd: workspace must be 8-byte aligned");
+    static const int rbps = std::max(1, env_int("B200_BN_REDUCE_BPS", 3));
     const int CG = C / 8;
-    dim3 grid(nblk, (CG + EW_THREADS - 1) / EW_THREADS);
-    bn_act_bwd_reduce_kernel<<<grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st>>>(a, (float*)ws);
+    dim3 grid(bn_blocks(rows, C, rbps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
+    double* accum = reinterpret_cast<double*>(ws);
+    launch_k(bn_act_bwd_reduce_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, reinterpret_cast<unsigned int*>(accum + BN_SLOTS * bn_slot_stride(C)));
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
-    bn_bwd_finalize_kernel<<<(C + FIN_CH_PER_BLOCK - 1) / FIN_CH_PER_BLOCK, FIN_THREADS, 0, st>>>((const float*)ws, nblk, C, dgamma, dbeta);
-    B200_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   }
   {
+    static const int abps = std::max(1, env_int("B200_BN_APPLY_BPS", 3));
     const int CG = C / 8;
-    const int CGb = std::min(EW_THREADS, CG);
-    const int RP = EW_THREADS / CGb;
-    int gx = (int)std::max<int64_t>(1, std::min<int64_t>((rows + (int64_t)RP * 2 - 1) / ((int64_t)RP * 2),
-                                                          (int64_t)num_sms() * 12));
-    dim3 grid(gx, (CG + EW_THREADS - 1) / EW_THREADS);
-    bn_act_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>(a);
+    dim3 grid(bn_blocks(rows, C, abps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
+    launch_k(bn_act_bwd_apply_kernel, grid, EW_THREADS, 0, st, a);
   }
   B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;
@@ -1155,8 +1171,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
 extern "C" int b200_subsample2(const void* x, void* y, int N, int H, int W, int C,
                                b200_stream_t stream) {
   B200_REQUIRE(x && y && C % 8 == 0, "subsample2: bad arguments");
-  subsample2_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)x, (bf16*)y, N, H, W, C);
+  launch_k(subsample2_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, N, H, W, C);
   B200_LAUNCH_CHECK("subsample2_kernel");
   return 0;
 }
@@ -1165,8 +1180,7 @@ extern "C" int b200_upsample_add(void* dx, const void* g, int N, int H, int W, i
                                  b200_stream_t stream) {
   B200_REQUIRE(dx && g && C % 8 == 0 && Cg % 8 == 0 && Cg <= C && ldg >= Cg && ldg % 8 == 0,
                "upsample_add: bad arguments");
-  upsample_add_kernel<<<ew_grid((size_t)N * H * W * Cg / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (bf16*)dx, (const bf16*)g, N, H, W, C, Cg, ldg);
+  launch_k(upsample_add_kernel, ew_grid((size_t)N * H * W * Cg / 8), EW_THREADS, 0, as_stream(stream), (bf16*)dx, (const bf16*)g, N, H, W, C, Cg, ldg);
   B200_LAUNCH_CHECK("upsample_add_kernel");
   return 0;
 }
@@ -1183,8 +1197,7 @@ extern "C" int b200_avgpool_fwd(const void* x, void* y, int N, int H, int W, int
                                 int pad, b200_stream_t stream) {
   B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "avgpool_fwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  avgpool_fwd_kernel<<<ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)x, (bf16*)y, d);
+  launch_k(avgpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, d);
   B200_LAUNCH_CHECK("avgpool_fwd_kernel");
   return 0;
 }
@@ -1193,8 +1206,7 @@ extern "C" int b200_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, i
                                 int stride, int pad, b200_stream_t stream) {
   B200_REQUIRE(dy && dx && C % 8 == 0 && stride >= 1, "avgpool_bwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  avgpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)dy, (bf16*)dx, d);
+  launch_k(avgpool_bwd_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)dy, (bf16*)dx, d);
   B200_LAUNCH_CHECK("avgpool_bwd_kernel");
   return 0;
 }
@@ -1203,8 +1215,7 @@ extern "C" int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int
                                 int pad, b200_stream_t stream) {
   B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "maxpool_fwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  maxpool_fwd_kernel<<<ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)x, (bf16*)y, d);
+  launch_k(maxpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, d);
   B200_LAUNCH_CHECK("maxpool_fwd_kernel");
   return 0;
 }
@@ -1213,8 +1224,7 @@ extern "C" int b200_maxpool_bwd(const void* dy, const void* x, const void* y, vo
                                 int W, int C, int k, int stride, int pad, b200_stream_t stream) {
   B200_REQUIRE(dy && x && y && dx && stride >= 1 && C % 8 == 0, "maxpool_bwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  maxpool_bwd_kernel<<<ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream)>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)y, (bf16*)dx, d);
+  launch_k(maxpool_bwd_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)dy, (const bf16*)x, (const bf16*)y, (bf16*)dx, d);
   B200_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;
 }
@@ -1226,7 +1236,7 @@ extern "C" int b200_linear_fwd(const void* x, const float* w, const float* b, vo
                                int I, int O, b200_stream_t stream) {
   B200_REQUIRE(x && w && logits, "linear_fwd: null pointer");
   const size_t threads = (size_t)B * O * 32;
-  linear_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>((const bf16*)x, w, b,
+  launch_k(linear_fwd_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream), (const bf16*)x, w, b,
                                                                               (bf16*)logits, B, I, O);
   B200_LAUNCH_CHECK("linear_fwd_kernel");
   return 0;
@@ -1237,13 +1247,11 @@ extern "C" int b200_linear_bwd(const void* dlogits, const void* x, const float* 
   B200_REQUIRE(dlogits && x && w, "linear_bwd: null pointer");
   cudaStream_t st = as_stream(stream);
   if (dx) {
-    linear_bwd_dx_kernel<<<(unsigned)(((size_t)B * I + 255) / 256), 256, 0, st>>>(
-        (const bf16*)dlogits, w, (bf16*)dx, B, I, O);
+    launch_k(linear_bwd_dx_kernel, (unsigned)(((size_t)B * I + 255) / 256), 256, 0, st, (const bf16*)dlogits, w, (bf16*)dx, B, I, O);
     B200_LAUNCH_CHECK("linear_bwd_dx_kernel");
   }
   if (dw) {
-    linear_bwd_dw_kernel<<<(unsigned)(((size_t)O * I + 255) / 256), 256, 0, st>>>(
-        (const bf16*)dlogits, (const bf16*)x, dw, db, B, I, O);
+    launch_k(linear_bwd_dw_kernel, (unsigned)(((size_t)O * I + 255) / 256), 256, 0, st, (const bf16*)dlogits, (const bf16*)x, dw, db, B, I, O);
     B200_LAUNCH_CHECK("linear_bwd_dw_kernel");
   }
   return 0;
@@ -1255,8 +1263,7 @@ extern "C" int b200_ce_topk(const void* logits, const int64_t* labels, float* ou
   cudaStream_t st = as_stream(stream);
   if (out) B200_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
   const size_t threads = (size_t)B * 32;
-  ce_topk_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-      (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
+  launch_k(ce_topk_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
   B200_LAUNCH_CHECK("ce_topk_kernel");
   return 0;
 }
@@ -1274,14 +1281,14 @@ extern "C" int b200_sgd_step(float* const* params, const float* const* grads, fl
             nesterov, first_step, inv_scale, found_inf, lr_ptr};
   const int64_t chunk = (int64_t)SGD_THREADS * SGD_VEC_PER_THREAD * 4;
   dim3 grid((unsigned)((max_size + chunk - 1) / chunk), n);
-  sgd_step_kernel<<<grid, SGD_THREADS, 0, as_stream(stream)>>>(a);
+  launch_k(sgd_step_kernel, grid, SGD_THREADS, 0, as_stream(stream), a);
   B200_LAUNCH_CHECK("sgd_step_kernel");
   return 0;
 }
 
 extern "C" int b200_tick(uint64_t* counter, b200_stream_t stream) {
   B200_REQUIRE(counter, "tick: null pointer");
-  tick_kernel<<<1, 1, 0, as_stream(stream)>>>(counter);
+  launch_k(tick_kernel, 1, 1, 0, as_stream(stream), counter);
   B200_LAUNCH_CHECK("tick_kernel");
   return 0;
 }

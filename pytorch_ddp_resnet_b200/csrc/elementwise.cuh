@@ -8,7 +8,6 @@
 namespace b200 {
 
 constexpr int EW_THREADS = 256;
-constexpr int BN_MAX_BLOCKS = 1024;
 
 // Inverted dropout on the 8 values of vector `v`: element j is dropped when its 16-bit uniform is
 // below drop_thr, else scaled by 1/(1-p) and (ROUND) rounded to bf16 like the reference's bf16 multiply.
@@ -32,11 +31,22 @@ __device__ __forceinline__ void dropout8(float* f, uint64_t seed, size_t v, uint
 // the whole kernel) and a row lane `rl`; acc[] holds NACC*8 per-channel partial sums of that thread.
 // The block reduces over row lanes and writes partial[blockIdx.x][a][C] for a < NACC.
 // -------------------------------------------------------------------------------------------------
+// Accumulator workspace of the reduction kernels: BN_SLOTS copies of fp64 [2][C], `slot_stride` doubles
+// apart (>= 4 KB so the copies land in different L2 slices), followed by the ticket counter. Block b adds
+// into copy b % BN_SLOTS: ncu showed ~600 blocks firing their atomics at the same few hundred addresses
+// in one burst took as long as the streaming loop itself (same-address atomics serialise in one slice).
+constexpr int BN_SLOTS = 8;
+__host__ __device__ __forceinline__ size_t bn_slot_stride(int C) {
+  const size_t need = 2 * (size_t)C;              // doubles
+  return (need < 512 ? 512 : (need + 31) / 32 * 32) + 32;
+}
+
 template <int NACC>
 __device__ __forceinline__ void block_channel_reduce(const float* acc, float* smem, int cgl, int rl,
-                                                     int CGb, int RP, bool active, float* partial,
+                                                     int CGb, int RP, bool active, double* accum,
                                                      int C, int c_base) {
-  // smem layout: [RP][CGb*8*NACC]
+  // smem layout: [RP][CGb*8*NACC]; the block total of every channel goes to its slot with one fp64
+  // atomic (fp32 inside a block: <= a few hundred terms; fp64 across blocks: E[x^2] - mean^2 cancels)
   const int width = CGb * 8 * NACC;
   if (active) {
 #pragma unroll
@@ -45,13 +55,44 @@ __device__ __forceinline__ void block_channel_reduce(const float* acc, float* sm
       for (int j = 0; j < 8; ++j) smem[rl * width + (a * CGb + cgl) * 8 + j] = acc[a * 8 + j];
   }
   __syncthreads();
+  double* slot = accum + (size_t)(blockIdx.x % BN_SLOTS) * bn_slot_stride(C);
   for (int i = threadIdx.x; i < width; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < RP; ++r) s += smem[r * width + i];
     const int a = i / (CGb * 8);
     const int c = c_base + (i % (CGb * 8));
-    partial[((size_t)blockIdx.x * NACC + a) * C + c] = s;
+    atomicAdd(slot + (size_t)a * C + c, (double)s);
   }
+}
+
+// Returns true in the block that finishes last; every other block's atomics are then visible to it
+// (barrier, then one thread fences and takes a ticket: the pattern of a cooperative grid sync).
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y;
+    is_last = atomicAdd(ticket, 1u) == total - 1u;
+    __threadfence();
+  }
+  __syncthreads();
+  return is_last != 0;
+}
+
+// sum of accumulator `a` of channel c over the slots; clears them
+__device__ __forceinline__ double drain_slots(double* accum, int C, int a, int c) {
+  const size_t stride = bn_slot_stride(C);
+  double v[BN_SLOTS];
+#pragma unroll
+  for (int k = 0; k < BN_SLOTS; ++k) v[k] = __ldcg(accum + k * stride + (size_t)a * C + c);
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < BN_SLOTS; ++k) {
+    s += v[k];
+    accum[k * stride + (size_t)a * C + c] = 0.0;
+  }
+  return s;
 }
 
 // geometry shared by the reduction kernels: blockIdx.y selects a chunk of <=256 channel groups
@@ -73,26 +114,47 @@ struct ReduceGeom {
   }
 };
 
-// partial[b][0][c] = sum x, partial[b][1][c] = sum x^2 over the rows of block b
-__global__ void __launch_bounds__(EW_THREADS)
-bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* __restrict__ partial) {
+struct BnStatsArgs {
+  const bf16* x;
+  int64_t rows;
+  int C;
+  float eps, momentum;
+  float* mean;
+  float* invstd;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  double* accum;          // BN_SLOTS x [2][C], zero on entry, zero again on exit
+  unsigned int* ticket;   // zero on entry, zero again on exit
+};
+
+// Batch statistics in ONE launch: every block adds its per-channel sum / sum of squares to the fp64
+// accumulators; the block that finishes last turns them into mean / invstd / running statistics and
+// clears the accumulators for the next call (no partial buffer, no finalize kernel).
+__global__ void __launch_bounds__(EW_THREADS, 4) bn_stats_kernel(const BnStatsArgs a) {
   extern __shared__ float red_smem[];
+  const int C = a.C;
   ReduceGeom g(C);
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   if (g.active) {
-    const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    constexpr int U = 8;   // 8 independent 16-byte loads in flight per thread; rows past r1 are skipped
+    const int64_t batch = (int64_t)g.RP * U;  // whole batches per block: no ragged extra round trip
+    const int64_t rows_per_block = ((a.rows + gridDim.x - 1) / gridDim.x + batch - 1) / batch * batch;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r1 = min(rows, r0 + rows_per_block);
-    const bf16* base = x + (size_t)(g.cg0 + g.cgl) * 8;
-    int64_t r = r0 + g.rl;
-    for (; r + 3 * (int64_t)g.RP < r1; r += 4 * (int64_t)g.RP) {
-      Vec8 v[4];
+    const int64_t r1 = min(a.rows, r0 + rows_per_block);
+    const bf16* base = a.x + (size_t)(g.cg0 + g.cgl) * 8;
+    for (int64_t r = r0 + g.rl; r < r1; r += U * (int64_t)g.RP) {
+      Vec8 v[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u].raw = ldg_stream(base + (size_t)(r + u * (int64_t)g.RP) * C);
+      for (int u = 0; u < U; ++u) {
+        const int64_t ru = r + u * (int64_t)g.RP;
+        v[u].raw = make_uint4(0u, 0u, 0u, 0u);
+        if (ru < r1) v[u].raw = ldg_stream(base + (size_t)ru * C);
+      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         float f[8];
         v[u].to_float(f);
 #pragma unroll
@@ -102,68 +164,25 @@ bn_stats_partial_kernel(const bf16* __restrict__ x, int64_t rows, int C, float* 
         }
       }
     }
-    for (; r < r1; r += g.RP) {
-      Vec8 v;
-      v.raw = ldg_stream(base + (size_t)r * C);
-      float f[8];
-      v.to_float(f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] += f[j];
-        acc[8 + j] = fmaf(f[j], f[j], acc[8 + j]);
-      }
+  }
+  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, a.accum, C, g.cg0 * 8);
+  if (!last_block_done(a.ticket)) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s = drain_slots(a.accum, C, 0, c), ss = drain_slots(a.accum, C, 1, c);
+    const double m = s / (double)a.rows;
+    double var = ss / (double)a.rows - m * m;
+    if (var < 0.0) var = 0.0;
+    a.mean[c] = (float)m;
+    a.invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
+    if (a.running_mean) {
+      const double unbiased = a.rows > 1 ? var * (double)a.rows / (double)(a.rows - 1) : var;
+      a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)m;
+      a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
     }
   }
-  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, C, g.cg0 * 8);
-}
-
-// Sum of the per-block partials of two quantities: one WARP per channel, lanes stride over the partial
-// blocks (independent loads, fully unrolled by the compiler), shuffle reduction in fp64.
-constexpr int FIN_THREADS = 256;
-constexpr int FIN_CH_PER_BLOCK = FIN_THREADS / 32;
-__device__ __forceinline__ bool finalize_sums(const float* __restrict__ partial, int nblk, int C,
-                                              int& c, double& s0, double& s1) {
-  c = blockIdx.x * FIN_CH_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return false;
-  float a = 0.f, b = 0.f;  // <= 10 terms per lane: fp32 is exact enough before the fp64 tree
-  double da = 0.0, db = 0.0;
-#pragma unroll 4
-  for (int k = lane; k < nblk; k += 32) {
-    a = __ldg(partial + ((size_t)k * 2 + 0) * C + c);
-    b = __ldg(partial + ((size_t)k * 2 + 1) * C + c);
-    da += (double)a;
-    db += (double)b;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    da += __shfl_xor_sync(0xffffffffu, da, o);
-    db += __shfl_xor_sync(0xffffffffu, db, o);
-  }
-  s0 = da;
-  s1 = db;
-  return lane == 0;
-}
-
-// mean / invstd from the partials (+ running-stat update, torch.nn.BatchNorm2d semantics)
-__global__ void __launch_bounds__(FIN_THREADS)
-bn_stats_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t rows, int C, float eps,
-                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                         float* __restrict__ running_mean, float* __restrict__ running_var,
-                         int64_t* __restrict__ num_batches_tracked) {
-  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  int c;
-  double s, ss;
-  if (!finalize_sums(partial, nblk, C, c, s, ss)) return;
-  const double m = s / (double)rows;
-  double var = ss / (double)rows - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  if (threadIdx.x == 0) {
+    *a.ticket = 0u;
+    if (a.num_batches_tracked) *a.num_batches_tracked += 1;
   }
 }
 
@@ -191,7 +210,8 @@ struct BnActFwdArgs {
 // Thread mapping of the element-wise BN kernels: a thread owns ONE 8-channel group for the whole
 // kernel (per-channel coefficients live in registers) and walks rows with stride RP * gridDim.x;
 // the RP x CGb threads of a block touch RP consecutive rows = one contiguous 4 KB span per pass.
-__global__ void __launch_bounds__(EW_THREADS, 3) bn_act_fwd_kernel(const BnActFwdArgs a) {
+template <int U, int MINB, bool SKIP>
+__global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnActFwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
   if (!g.active) return;
@@ -208,17 +228,16 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_fwd_kernel(const BnActFw
   }
   const int64_t rows = (int64_t)a.N * a.H * a.W;
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
-  const bool skip_here = a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C);
+  const bool skip_here = SKIP && (a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C));
   const int64_t stride = (int64_t)g.RP * gridDim.x;
-  constexpr int U = 2;
   for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < rows; r0 += U * stride) {
-    Vec8 xv[U], sv[U];
+    Vec8 xv[U], sv[SKIP ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = r0 + u * stride;
       if (r < rows) {
         xv[u].raw = ldg_stream(a.x + ((size_t)r * g.CG + cgi) * 8);
-        if (skip_here) {
+        if (SKIP && skip_here) {
           size_t so;
           if (a.skip_mode == 1) {
             so = ((size_t)r * g.CG + cgi) * 8;
@@ -228,7 +247,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_fwd_kernel(const BnActFw
             const int n = (int)(r / ((int64_t)a.W * a.H));
             so = (((size_t)n * (2 * a.H) + 2 * h) * (2 * a.W) + 2 * w) * a.skip_C + (size_t)cgi * 8;
           }
-          sv[u].raw = ldg_stream(a.skip + so);
+          sv[SKIP ? u : 0].raw = ldg_stream(a.skip + so);
         }
       }
     }
@@ -243,9 +262,9 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_fwd_kernel(const BnActFw
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = round_bf16(fmaf(f[j], sc[j], sh[j]));
       }
-      if (skip_here) {
+      if (SKIP && skip_here) {
         float sk[8];
-        sv[u].to_float(sk);
+        sv[SKIP ? u : 0].to_float(sk);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + sk[j]);
       }
@@ -306,9 +325,9 @@ __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t
   }
 }
 
-// partial[b][0][c] = sum g, partial[b][1][c] = sum g * xhat
+// accum[0][c] += sum g, accum[1][c] += sum g * xhat; the last block writes dbeta / dgamma and clears accum
 __global__ void __launch_bounds__(EW_THREADS, 3)
-bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
+bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsigned int* ticket) {
   extern __shared__ float red_smem[];
   ReduceGeom g(a.C);
   float acc[16];
@@ -323,10 +342,11 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
       mu[j] = a.mean[cgi * 8 + j];
       is[j] = a.invstd[cgi * 8 + j];
     }
-    const int64_t rows_per_block = (a.rows + gridDim.x - 1) / gridDim.x;
+    constexpr int U = 2;
+    const int64_t batch = (int64_t)g.RP * U;
+    const int64_t rows_per_block = ((a.rows + gridDim.x - 1) / gridDim.x + batch - 1) / batch * batch;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(a.rows, r0 + rows_per_block);
-    constexpr int U = 2;
     for (int64_t rb = r0 + g.rl; rb < r1; rb += U * (int64_t)g.RP) {
       Vec8 dv[U], yv[U], xv[U];
 #pragma unroll
@@ -355,18 +375,13 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, float* __restrict__ partial) {
       }
     }
   }
-  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, partial, a.C,
-                          g.cg0 * 8);
-}
-
-__global__ void __launch_bounds__(FIN_THREADS)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
-  int c;
-  double s, sx;
-  if (!finalize_sums(partial, nblk, C, c, s, sx)) return;
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)sx;
+  block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, accum, a.C, g.cg0 * 8);
+  if (!last_block_done(ticket)) return;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    a.dbeta[c] = (float)drain_slots(accum, a.C, 0, c);
+    a.dgamma[c] = (float)drain_slots(accum, a.C, 1, c);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g.

@@ -29,6 +29,25 @@ def step_counter(device: torch.device) -> torch.Tensor:
     return t
 
 
+_bn_accums = {}
+
+
+def bn_accumulators(device: torch.device, nbytes: int = 0) -> torch.Tensor:
+    """Zero-filled fp64 accumulators + ticket counter of b200_bn_stats / b200_bn_act_bwd (see
+    include/b200resnet.h: zero on entry, zero again on exit). One buffer per (device, stream); all
+    capturing streams of a device share one buffer that is created before any capture starts (by the
+    first eager call, or by GraphedTrainStep), so that no fill kernel is recorded into a graph."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (device.index, "capture" if capturing else _stream())
+    t = _bn_accums.get(key)
+    if t is None or t.numel() * 8 < nbytes:
+        t = torch.zeros(max(1 << 15, (nbytes + 7) // 8), dtype=torch.float64, device=device)
+        _bn_accums[key] = t
+        if not capturing and (device.index, "capture") not in _bn_accums:
+            _bn_accums[(device.index, "capture")] = torch.zeros_like(t)
+    return t
+
+
 def tick(device: torch.device) -> None:
     _lib.require_device(device.index or 0)
     _lib.call("b200_tick", step_counter(device).data_ptr(), _stream())
@@ -235,7 +254,7 @@ def bn_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_va
     mean = torch.empty((C,), dtype=torch.float32, device=x.device)
     invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
     nws = _lib.load().b200_bn_workspace_bytes(rows, C)
-    ws = _workspace(x.device, nws)
+    ws = bn_accumulators(x.device, nws)
     _lib.call("b200_bn_stats", x.data_ptr(), rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
               _p(running_mean), _p(running_var), _p(num_batches_tracked), ws.data_ptr(), nws, _stream())
     return mean, invstd
@@ -274,7 +293,7 @@ def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = Tru
     dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
     dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
     nws = _lib.load().b200_bn_workspace_bytes(rows, C) if affine else 0
-    ws = _workspace(dy.device, nws) if affine else None
+    ws = bn_accumulators(dy.device, nws) if affine else None
     if addend is not None:
         _check_act(addend, "bn_act_bwd.addend")
         assert addend.shape == dy.shape

@@ -51,6 +51,8 @@ class GraphedTrainStep:
         if self.is_ddp:
             self._setup_flat_gradients()
         ops.step_counter(self.device)  # must exist before capture (an in-capture alloc would re-zero it)
+        with torch.cuda.device(self.device):
+            ops.bn_accumulators(self.device)  # likewise: zero-filled once, outside the graph
         self.graph = torch.cuda.CUDAGraph()
         classifier.train()
         side = torch.cuda.Stream(device=self.device)
