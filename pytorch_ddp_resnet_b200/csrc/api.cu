@@ -69,6 +69,11 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -395,15 +400,15 @@ static bool conv_use_halo() {
   return v != 0;
 }
 
-// make_tmap_nhwc with an explicit box (the halo patch is wider / taller than the output tile)
-template <int KC>
+// Halo-reuse SM-pair launch (see conv_tc2h_kernel). MT pixel tiles per CTA share each filter stage.
+template <int KC, int MT>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                             int wcols, const TapTable& taps, void* out, const void* residual,
-                            const float* bias, int Nimg, int P, int Q, int BN, cudaStream_t st) {
+                            const float* bias, int Nimg, int P, int Q, int BN, int pw, cudaStream_t st) {
   static bool attr_set = false;
   const int max_dyn = 228352;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    max_dyn));
     attr_set = true;
   }
@@ -414,9 +419,11 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
   a.num_tiles = a.tiles_w * a.tiles_h * Nimg * a.n_ntiles;
   a.ntaps = taps.n;
-  a.patch_bytes = (uint32_t)HALO_PW * HALO_PH * KC * 2u;
+  a.pw = pw;
+  a.patch_tx_bytes = (uint32_t)pw * HALO_PH * KC * 2u;
+  a.patch_bytes = (a.patch_tx_bytes + 1023u) & ~1023u;
   a.btile_bytes = (((uint32_t)(BN / 2) * KC * 2u) + 1023u) & ~1023u;
-  const int budget = max_dyn - 1024 - 2 * (int)a.patch_bytes;
+  const int budget = max_dyn - 1024 - 2 * MT * (int)a.patch_bytes;
   // taps per filter stage: all 9 when three such stages fit (>= 18 MMAs per barrier round trip), else 3
   a.tpb = (budget / (int)(taps.n * a.btile_bytes) >= 3) ? taps.n : 3;
   if (const char* e = getenv("B200_HALO_TPB")) a.tpb = std::max(1, std::min(atoi(e), taps.n));
@@ -425,22 +432,22 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.bstages = std::min(HALO_BSTAGES_MAX, budget / (int)a.bstage_bytes);
   B200_REQUIRE(a.bstages >= 2, "conv_tc2h: filter ring does not fit in shared memory");
   for (int t = 0; t < taps.n; ++t) {
-    a.tap_rowoff[t] = (taps.dh[t] + 1) * HALO_PW + (taps.dw[t] + 1);
+    a.tap_rowoff[t] = (taps.dh[t] + 1) * pw + (taps.dw[t] + 1);
     a.tap_wcol[t] = taps.wcol[t];
   }
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
   CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, HALO_PW, HALO_PH, 1)) return rc;
+  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, pw, HALO_PH, 1)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
-  size_t dyn = 2 * (size_t)a.patch_bytes + (size_t)a.bstages * a.bstage_bytes + 1024;
+  size_t dyn = 2 * MT * (size_t)a.patch_bytes + (size_t)a.bstages * a.bstage_bytes + 1024;
   dyn = std::max<size_t>(dyn, 120 * 1024);
-  const int num_ptiles = a.num_tiles / 2;
-  const int grid = std::min(num_ptiles, num_sms() / 2) * 2;
+  const int num_units = a.num_tiles / (2 * MT);
+  const int grid = std::min(num_units, num_sms() / 2) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(64 + 128 * MT);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -450,7 +457,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC>, tmA, tmB, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC, MT>, tmA, tmB, a));
   B200_LAUNCH_CHECK("conv_tc2h_kernel");
   return 0;
 }
@@ -500,11 +507,16 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
     const int mt8x16 = (Q / 8) * (P / 16) * Nimg;
     if (unit && conv_use_halo() && conv_use_pair() && Q % 8 == 0 && P % 16 == 0 && mt8x16 % 2 == 0 &&
         BN % 32 == 0 && Cin % KC == 0 && KC >= 32) {
-      if (KC == 64)
-        return launch_conv_tc2h<64>(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias,
-                                    Nimg, P, Q, BN, st);
-      return launch_conv_tc2h<32>(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias,
-                                  Nimg, P, Q, BN, st);
+      // B200_HALO_MT = 1 | 2, B200_HALO_PW = 10 | 16. Measured (round 1, fprop TFLOP/s, 160@32x32 /
+      // 320@16x16): MT=1 1183 / 1419, MT=2 983 / 1163 (halved filter traffic does not pay for the lost
+      // accumulator double-buffering: the kernel is not L2->SM bound), PW=16 1168 / 1414.
+      static const int mt_env = env_int("B200_HALO_MT", 1);
+      static const int pw = std::max(10, std::min(16, env_int("B200_HALO_PW", 10)));
+      const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512;
+#define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw, st
+      if (KC == 64) return mt2 ? launch_conv_tc2h<64, 2>(B200_HALO_ARGS) : launch_conv_tc2h<64, 1>(B200_HALO_ARGS);
+      return mt2 ? launch_conv_tc2h<32, 2>(B200_HALO_ARGS) : launch_conv_tc2h<32, 1>(B200_HALO_ARGS);
+#undef B200_HALO_ARGS
     }
   }
   a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = (Cin + KC - 1) / KC; a.cin = Cin;
@@ -776,22 +788,22 @@ static int launch_wgrad_tc_cs(int cs, int mt, const CUtensorMap& tmX, const CUte
   }
 }
 
-// pixel-range splits: fill whole waves of the SMs (a 2.2-wave grid idles 30 % of the machine)
-static int pick_wgrad_splits(int cols, int num_ptiles) {
+// Pixel-range splits of a wgrad launch. Cost model in units of one pipeline stage:
+//   time(sp) = waves(cols * sp CTAs) * (stages per CTA + fixed), fixed = prologue + TMEM drain with
+// atomics + launch tail expressed in stages. Minimising it fills whole waves of the SMs without paying
+// the fixed part more often than needed (a 2-wave grid of half-length CTAs is slower than a 1-wave one).
+static int pick_wgrad_splits(int cols, int num_ptiles, int fixed_units) {
   const int sms = num_sms();
   int best = 1;
-  double best_score = -1.0;
+  double best_cost = 1e30;
   const int max_splits = std::min(num_ptiles, 64);
   for (int sp = 1; sp <= max_splits; ++sp) {
     const int per = (num_ptiles + sp - 1) / sp;
     if ((num_ptiles + per - 1) / per != sp) continue;  // would leave empty splits
     const long total = (long)cols * sp;
     const long waves = (total + sms - 1) / sms;
-    double eff = (double)total / (double)(waves * sms);
-    if (per < 8) eff *= 0.85;              // short main loops pay prologue / epilogue overhead
-    if (total < sms) eff *= 0.9;
-    const double score = eff - 0.002 * sp;  // fewer atomics when equal
-    if (score > best_score) { best_score = score; best = sp; }
+    const double cost = (double)waves * (per + fixed_units) * (1.0 + 0.001 * sp);  // ties: fewer atomics
+    if (cost < best_cost) { best_cost = cost; best = sp; }
   }
   if (const char* e = getenv("B200_WGRAD_SPLITS")) best = std::max(1, std::min(atoi(e), num_ptiles));
   const int per = (num_ptiles + best - 1) / best;
@@ -822,7 +834,7 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   const int BN = pick_bn(K, 32, 160);
   if (BN <= 0) return -1;
   int pw = 10;
-  if (const char* e = getenv("B200_WGRAD_PW")) pw = std::max(10, std::min(16, atoi(e)));
+  if (const char* e = getenv("B200_WGRAD_PW")) pw = (atoi(e) == 16) ? 16 : 10;  // box bytes stay 1 KB multiples
   WgradHaloArgs a;
   memset(&a, 0, sizeof(a));
   a.bh = bh; a.bn = bn; a.pw = pw;
@@ -840,7 +852,7 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   a.stages = std::min<int>(WGH_STAGES_MAX, (max_dyn - 1024) / (int)a.stage_bytes);
   if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
   if (a.stages < 2) return -1;
-  a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles);
+  a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles, 5);
   for (int t = 0; t < 9; ++t) a.wcol[t] = taps.wcol[t];
   a.dw = dw;
   static bool attr_set = false;
@@ -921,7 +933,7 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   a.nb = (BN + SL - 1) / SL;
   a.ktot = taps.n * C;
   const int cols = a.n_mgroups * a.n_ntiles;
-  a.splits = pick_wgrad_splits(cols, a.num_ptiles);
+  a.splits = pick_wgrad_splits(cols, a.num_ptiles, 8);
   a.taps = taps;
   a.dw = dw;
   if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
@@ -1036,11 +1048,6 @@ extern "C" int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C,
 // -------------------------------------------------------------------------------------------------
 // Grids of the HBM-bound BN kernels are ONE wave of resident blocks (measured: 1776 short blocks reach
 // 4.0 TB/s on the 42 MB tensors, 592 long-lived ones with 4 loads in flight per thread 5.3 TB/s).
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 // One wave of at most num_sms * blocks_per_sm blocks in which every thread walks the same whole number
 // of `unroll`-row batches (a ragged last batch is a full extra memory round trip for the whole grid).
 static int bn_blocks(int64_t rows, int C, int blocks_per_sm, int unroll) {

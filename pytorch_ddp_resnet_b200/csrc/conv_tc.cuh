@@ -481,7 +481,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // base_offset = 0). Activation traffic through TMA drops from 9 x 16 KB to 36 KB per K-block; the per-tap
 // filter tiles stream through their own ring (several taps per stage).
 // -------------------------------------------------------------------------------------------------
-constexpr int HALO_PW = 16;   // patch pitch in pixels (8 + 2 halo, padded to a multiple of 8)
 constexpr int HALO_PH = 18;   // patch rows (16 + 2 halo)
 constexpr int HALO_BSTAGES_MAX = 8;
 
@@ -491,19 +490,26 @@ struct ConvHaloArgs {
   int P, Q, Nimg, ldo;
   int num_tiles;                    // pixel tiles x channel tiles (even count of pixel tiles)
   int ntaps, tpb, ntg;              // taps, taps per filter stage, filter stages per K-block
+  int pw;                           // patch width in pixels (10: tile + halo; 16: padded to 2 swizzle atoms)
   int bstages;
-  uint32_t patch_bytes, btile_bytes, bstage_bytes;
-  int tap_rowoff[TC_MAX_TAPS];      // (dh + 1) * HALO_PW + (dw + 1)
+  uint32_t patch_bytes, btile_bytes, bstage_bytes;  // slot strides (1 KB multiples)
+  uint32_t patch_tx_bytes;          // bytes one patch box delivers (pw * 18 * KC * 2)
+  int tap_rowoff[TC_MAX_TAPS];      // (dh + 1) * pw + (dw + 1)
   int tap_wcol[TC_MAX_TAPS];
   bf16* out;
   const bf16* residual;
   const float* bias;
 };
 
-template <int KC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
+// buffered when MT = 2, epilogue with 4 warps PER TILE). ncu on MT = 1: 330 MB per launch through the
+// L2->SM path, 236 MB of it the same filter tiles fetched once per tile pair; MT = 2 halves that but was
+// measured SLOWER (983 vs 1183 TFLOP/s at 160 channels): kept for experiments, default MT = 1.
+template <int KC, int MT>
+__global__ void __launch_bounds__(64 + 128 * MT, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvHaloArgs args) {
+  constexpr int NBUF = (MT == 1) ? 2 : 1;   // accumulator sets
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t pfull_bar[2], pempty_bar[2];
   __shared__ uint64_t bfull_bar[HALO_BSTAGES_MAX], bempty_bar[HALO_BSTAGES_MAX];
@@ -514,7 +520,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
-  uint8_t* bring = smem + 2 * (size_t)args.patch_bytes;
+  const uint32_t pslot_bytes = MT * args.patch_bytes;
+  uint8_t* bring = smem + 2 * (size_t)pslot_bytes;
   const int crank = (int)cluster_ctarank();
   const bool leader = crank == 0;
 
@@ -525,7 +532,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&pfull_bar[i], 1);
       mbar_init(&pempty_bar[i], 1);
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], 8 * MT);
     }
     for (int i = 0; i < args.bstages; ++i) {
       mbar_init(&bfull_bar[i], 1);
@@ -546,26 +553,31 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_img = args.tiles_w * args.tiles_h;
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int num_ptiles = args.num_tiles >> 1;
+  const int num_units = args.num_tiles / (2 * MT);   // one unit = MT pixel tiles per CTA of the pair
   const int bhalf = args.BN >> 1;
+  const int pw = args.pw;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int ps = 0, bs = 0;
     uint32_t pph = 0, bph = 0;
-    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+    for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
-      const int mt = (ct / args.n_ntiles) * 2 + crank;
-      const int w0 = (mt % args.tiles_w) * 8;
-      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * 16;
-      const int n0 = mt / tiles_img;
+      const int mt0 = ((ct / args.n_ntiles) * 2 + crank) * MT;
       for (int kc = 0; kc < args.nkc; ++kc) {
         mbar_wait(&pempty_bar[ps], pph ^ 1);
         if (elect_one()) {
           const uint32_t pfull_leader = map_to_cta(smem_u32(&pfull_bar[ps]), 0);
-          if (leader) mbar_expect_tx(&pfull_bar[ps], 2u * args.patch_bytes);
-          tma_load_4d_2sm(smem + (size_t)ps * args.patch_bytes, &tmA, pfull_leader, kc * KC, w0 - 1,
-                          h0 - 1, n0);
+          if (leader) mbar_expect_tx(&pfull_bar[ps], 2u * MT * args.patch_tx_bytes);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const int mt = mt0 + t;
+            const int w0 = (mt % args.tiles_w) * 8;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * 16;
+            const int n0 = mt / tiles_img;
+            tma_load_4d_2sm(smem + (size_t)ps * pslot_bytes + (size_t)t * args.patch_bytes, &tmA,
+                            pfull_leader, kc * KC, w0 - 1, h0 - 1, n0);
+          }
         }
         __syncwarp();
         if (++ps == 2) { ps = 0; pph ^= 1; }
@@ -591,20 +603,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ===================== MMA issuer (leader CTA only) =====================
       const uint32_t idesc = make_idesc_bf16(256, args.BN, 0, 0);
       const uint32_t bhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
-      const uint32_t ahi = smem_desc_hi(HALO_PW * KMajorCfg<KC>::ROW_BYTES, KMajorCfg<KC>::LAYOUT);
+      const uint32_t ahi = smem_desc_hi((uint32_t)pw * KMajorCfg<KC>::ROW_BYTES, KMajorCfg<KC>::LAYOUT);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t bring_base = smem_u32(bring);
       const uint32_t bstep = args.btile_bytes >> 4;
+      const uint32_t pstep = args.patch_bytes >> 4;
       int ps = 0, bs = 0, as = 0;
       uint32_t pph = 0, bph = 0, aph = 0;
-      for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      for (int ct = pair_id; ct < num_units; ct += num_pairs) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
         uint32_t acc = 0;
         for (int kc = 0; kc < args.nkc; ++kc) {
           mbar_wait(&pfull_bar[ps], pph);
-          const uint32_t patch_lo = smem_desc_lo(smem_base + (uint32_t)ps * args.patch_bytes, 16);
+          const uint32_t patch_lo = smem_desc_lo(smem_base + (uint32_t)ps * pslot_bytes, 16);
           for (int tg = 0; tg < args.ntg; ++tg) {
             mbar_wait(&bfull_bar[bs], bph);
             tc_fence_after();
@@ -617,8 +630,11 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     patch_lo + (((uint32_t)args.tap_rowoff[t0 + j] * KMajorCfg<KC>::ROW_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, ahi),
-                                   smem_desc_join(blo + 2 * k, bhi), idesc, acc);
+                  const uint64_t bd = smem_desc_join(blo + 2 * k, bhi);
+#pragma unroll
+                  for (int t = 0; t < MT; ++t)
+                    umma_bf16_ss_2sm(d_addr + (uint32_t)(t * args.BN),
+                                     smem_desc_join(alo + t * pstep + 2 * k, ahi), bd, idesc, acc);
                   acc = 1u;
                 }
                 blo += bstep;
@@ -634,21 +650,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++ps == 2) { ps = 0; pph ^= 1; }
         }
-        as ^= 1;
-        if (as == 0) aph ^= 1;
+        if (++as == NBUF) { as = 0; aph ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (both CTAs, own TMEM, own 8x16 pixel tile) =====================
-    const int wq = warp & 3;
+    // ===================== epilogue (both CTAs, own TMEM): 4 warps per pixel tile =====================
+    const int wq = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int t = (warp - 2) >> 2;           // pixel tile of this CTA handled by this warp
     const int m = wq * 32 + lane;
     const int wi = m & 7;
     const int hi = m >> 3;
     int as = 0;
     uint32_t aph = 0;
-    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+    for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
-      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int mt = ((ct / args.n_ntiles) * 2 + crank) * MT + t;
       const int w = (mt % args.tiles_w) * 8 + wi;
       const int h = ((mt / args.tiles_w) % args.tiles_h) * 16 + hi;
       const int n = mt / tiles_img;
@@ -660,7 +676,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
+      const uint32_t t_addr =
+          tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u + (uint32_t)(t * args.BN);
       for (int c = 0; c < args.BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
@@ -691,8 +708,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
-      as ^= 1;
-      if (as == 0) aph ^= 1;
+      if (++as == NBUF) { as = 0; aph ^= 1; }
     }
   }
 
