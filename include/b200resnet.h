@@ -76,6 +76,17 @@ int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias, cons
                       void* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
                       int algo, void* ws, size_t ws_bytes, b200_stream_t stream);
 
+/* b200_conv2d_fprop that ALSO adds, per output channel k, sum(y[..,k]) and sum(y[..,k]^2) over all
+ * N*P*Q output pixels (of the bf16 values it stores) into the BN accumulator workspace `stats_ws`
+ * (b200_bn_workspace_bytes(rows, K) bytes, contract below: zero on entry). The batch norm that follows a
+ * conv in the reference (residual_block.py:69-98) then needs no pass of its own over y: call
+ * b200_bn_stats_finalize on the same workspace. The tcgen05 SM-pair kernels do this in their epilogue;
+ * other conv paths run one accumulate-only reduction over y, so the result is the same either way. */
+int b200_conv2d_fprop_stats(const void* x, const void* w_krsc, const float* bias, const void* residual,
+                            void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
+                            int pad, int algo, void* ws, size_t ws_bytes, void* stats_ws,
+                            size_t stats_ws_bytes, b200_stream_t stream);
+
 /* dx = bf16( conv_transpose(dy, w) ) ; if addend: dx = bf16(dx + addend) (skip-path gradient).
  * w_crsk is the transposed bf16 filter from b200_weight_prep. */
 int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx, int N, int H,
@@ -93,8 +104,8 @@ int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int
 
 /* ---- batch norm + activation + dropout + skip (aten::native_batch_norm, relu, native_dropout, add,
  * constant_pad_nd, avg_pool2d(k=1,s=2); residual_block.py:58-65,69-98,175-214; resnet.py:111-115) -- */
-/* Size of the ACCUMULATOR workspace of b200_bn_stats / b200_bn_act_bwd: fp64 [2][C] sums + a ticket
- * counter. Contract: 8-byte aligned, zero-filled before its first use, not shared between streams that
+/* Size of the ACCUMULATOR workspace of b200_bn_stats / b200_bn_act_bwd / b200_conv2d_fprop_stats:
+ * several copies of fp64 [2][C] sums (spread over L2 slices) + a ticket counter. Contract: 8-byte aligned, zero-filled before its first use, not shared between streams that
  * run concurrently; every call leaves it zero-filled again (the block that finishes last folds the sums
  * into the outputs and clears them), so one cudaMemset when it is allocated is all a caller needs. */
 size_t b200_bn_workspace_bytes(int64_t rows, int C);
@@ -105,6 +116,13 @@ size_t b200_bn_workspace_bytes(int64_t rows, int C);
 int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum, float* mean,
                   float* invstd, float* running_mean, float* running_var,
                   int64_t* num_batches_tracked, void* ws, size_t ws_bytes, b200_stream_t stream);
+
+/* Second half of b200_bn_stats for sums that b200_conv2d_fprop_stats left in `ws`: mean / invstd
+ * (+ running statistics, num_batches_tracked) from the accumulated sums of `rows` values per channel;
+ * clears the workspace. */
+int b200_bn_stats_finalize(int64_t rows, int C, float eps, float momentum, float* mean, float* invstd,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                           void* ws, size_t ws_bytes, b200_stream_t stream);
 
 /* y = dropout( act( (x - mean) * invstd * gamma + beta [+ skip] ) ).
  * stat_is_var != 0: `invstd` holds a variance (eval mode, running stats) and rsqrt(var+eps) is applied.

@@ -260,7 +260,8 @@ class TopConvFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, mod: Conv2d):
         xh = as_nhwc(x)
         wk, wt = mod.working_copies()
-        y = ops.conv_fprop(xh, wk, mod.stride, mod.padding, bias=bias)
+        # the stem is followed by a batch norm (first block / `n` token): sum its statistics here
+        y = ops.conv_fprop(xh, wk, mod.stride, mod.padding, bias=bias, want_stats=mod.training)
         ctx.mod = mod
         ctx.need_dx = x.requires_grad
         ctx.x_dtype, ctx.x_cl = x.dtype, x.permute(0, 2, 3, 1).is_contiguous()

@@ -71,10 +71,13 @@ class _BlockFn(torch.autograd.Function):
                 saved_in.append(h)          # BN input
                 saved_act.append(a)         # conv input
                 stats.append(st)
+                # training: the output of these convs feeds a batch norm next (bn j+1 of this block, or
+                # the first norm after the block), so its statistics are summed in the conv epilogue
                 if j < n - 1:
-                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding)
+                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding, want_stats=training)
                 elif skip_mode == _lib.SKIP_SAME:
-                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding, residual=skip)
+                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding, residual=skip,
+                                       want_stats=training)
                 else:
                     h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding)
                     h = ops.bn_act_fwd(h, relu=False, skip=skip, skip_mode=skip_mode)
@@ -82,7 +85,7 @@ class _BlockFn(torch.autograd.Function):
         else:
             for j, c in enumerate(convs):
                 d = ops.bn_act_fwd(h, relu=False, dropout_p=p, seed=seeds[j]) if p > 0.0 else h
-                cj = ops.conv_fprop(d, wk[j][0], c.stride, c.padding)
+                cj = ops.conv_fprop(d, wk[j][0], c.stride, c.padding, want_stats=training)
                 st = bn_args(j, cj)
                 saved_act.append(d)         # conv input
                 saved_conv.append(cj)       # BN input

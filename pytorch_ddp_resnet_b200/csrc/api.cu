@@ -344,13 +344,13 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
 }
 
 // SM-pair (cta_group::2) launch: tmB's box holds BN/2 filter rows
-template <int KC>
+template <int KC, bool STATS>
 static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                            cudaStream_t st) {
   static bool attr_set = false;
   const int max_dyn = 228352;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    max_dyn));
     attr_set = true;
   }
@@ -385,7 +385,7 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<KC>, tmA, tmB, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<KC, STATS>, tmA, tmB, a));
   B200_LAUNCH_CHECK("conv_tc2_kernel");
   return 0;
 }
@@ -401,14 +401,15 @@ static bool conv_use_halo() {
 }
 
 // Halo-reuse SM-pair launch (see conv_tc2h_kernel). MT pixel tiles per CTA share each filter stage.
-template <int KC, int MT>
+template <int KC, int MT, bool STATS>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                             int wcols, const TapTable& taps, void* out, const void* residual,
-                            const float* bias, int Nimg, int P, int Q, int BN, int pw, cudaStream_t st) {
+                            const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
+                            cudaStream_t st) {
   static bool attr_set = false;
   const int max_dyn = 228352;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC, MT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    max_dyn));
     attr_set = true;
   }
@@ -438,6 +439,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
+  a.stats = stats;
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, pw, HALO_PH, 1)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
@@ -457,7 +459,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC, MT>, tmA, tmB, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC, MT, STATS>, tmA, tmB, a));
   B200_LAUNCH_CHECK("conv_tc2h_kernel");
   return 0;
 }
@@ -486,7 +488,11 @@ static int launch_conv_tc_cs(int cs, const CUtensorMap& tmA, const CUtensorMap& 
 // out: [Nimg][P][Q][Cout].
 static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                        int wcols, const TapTable& taps, void* out, const void* residual,
-                       const float* bias, int Nimg, int P, int Q, cudaStream_t st) {
+                       const float* bias, int Nimg, int P, int Q, cudaStream_t st,
+                       double* stats = nullptr, bool* stats_fused = nullptr) {
+  // stats != nullptr: the SM-pair kernels also accumulate the per-channel sum / sum of squares of the
+  // output (fused BN statistics); *stats_fused says whether the kernel that ran did it
+  if (stats_fused) *stats_fused = false;
   int KC = pick_kc(Cin);
   const int BN = pick_bn(Cout, 16, 256);
   B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
@@ -513,9 +519,17 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       static const int mt_env = env_int("B200_HALO_MT", 1);
       static const int pw = std::max(10, std::min(16, env_int("B200_HALO_PW", 10)));
       const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512;
-#define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw, st
-      if (KC == 64) return mt2 ? launch_conv_tc2h<64, 2>(B200_HALO_ARGS) : launch_conv_tc2h<64, 1>(B200_HALO_ARGS);
-      return mt2 ? launch_conv_tc2h<32, 2>(B200_HALO_ARGS) : launch_conv_tc2h<32, 1>(B200_HALO_ARGS);
+#define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw
+      if (stats && !mt2 && BN <= EPI_STATS_MAX_BN) {
+        *stats_fused = true;
+        if (KC == 64) return launch_conv_tc2h<64, 1, true>(B200_HALO_ARGS, stats, st);
+        return launch_conv_tc2h<32, 1, true>(B200_HALO_ARGS, stats, st);
+      }
+      if (KC == 64)
+        return mt2 ? launch_conv_tc2h<64, 2, false>(B200_HALO_ARGS, nullptr, st)
+                   : launch_conv_tc2h<64, 1, false>(B200_HALO_ARGS, nullptr, st);
+      return mt2 ? launch_conv_tc2h<32, 2, false>(B200_HALO_ARGS, nullptr, st)
+                 : launch_conv_tc2h<32, 1, false>(B200_HALO_ARGS, nullptr, st);
 #undef B200_HALO_ARGS
     }
   }
@@ -533,10 +547,19 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
     if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
+    if (stats && BN <= EPI_STATS_MAX_BN) {
+      *stats_fused = true;
+      a.stats = stats;
+      switch (KC) {
+        case 64: return launch_conv_tc2<64, true>(tmA, tmB, a, st);
+        case 32: return launch_conv_tc2<32, true>(tmA, tmB, a, st);
+        default: return launch_conv_tc2<16, true>(tmA, tmB, a, st);
+      }
+    }
     switch (KC) {
-      case 64: return launch_conv_tc2<64>(tmA, tmB, a, st);
-      case 32: return launch_conv_tc2<32>(tmA, tmB, a, st);
-      default: return launch_conv_tc2<16>(tmA, tmB, a, st);
+      case 64: return launch_conv_tc2<64, false>(tmA, tmB, a, st);
+      case 32: return launch_conv_tc2<32, false>(tmA, tmB, a, st);
+      default: return launch_conv_tc2<16, false>(tmA, tmB, a, st);
     }
   }
   // cluster size: the pixel-tile count must split evenly and every filter slice must be whole 8-row
@@ -573,10 +596,10 @@ static TapTable fprop_taps(int N, int C, int R, int S, int stride, int pad) {
   return tt;
 }
 
-extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
-                                 const void* residual, void* y, int N, int H, int W, int C, int K,
-                                 int R, int S, int stride, int pad, int algo, void* ws,
-                                 size_t ws_bytes, b200_stream_t stream) {
+static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bias,
+                             const void* residual, void* y, int N, int H, int W, int C, int K,
+                             int R, int S, int stride, int pad, int algo, void* ws,
+                             size_t ws_bytes, b200_stream_t stream, double* stats, bool* stats_fused) {
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -596,7 +619,8 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
-    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st);
+    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, stats,
+                       stats_fused);
   }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {
@@ -617,7 +641,40 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
     act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
   }
   TapTable tt = fprop_taps(N, C, R, S, stride, pad);
-  return run_conv_tc(act, Nact, Ha, Wa, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st);
+  return run_conv_tc(act, Nact, Ha, Wa, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, stats,
+                     stats_fused);
+}
+
+extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
+                                 const void* residual, void* y, int N, int H, int W, int C, int K,
+                                 int R, int S, int stride, int pad, int algo, void* ws,
+                                 size_t ws_bytes, b200_stream_t stream) {
+  bool fused = false;
+  return conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
+                           ws_bytes, stream, nullptr, &fused);
+}
+
+static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t ws_bytes, int finalize,
+                          float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, cudaStream_t st);
+
+extern "C" int b200_conv2d_fprop_stats(const void* x, const void* w_krsc, const float* bias,
+                                       const void* residual, void* y, int N, int H, int W, int C, int K,
+                                       int R, int S, int stride, int pad, int algo, void* ws,
+                                       size_t ws_bytes, void* stats_ws, size_t stats_ws_bytes,
+                                       b200_stream_t stream) {
+  B200_REQUIRE(stats_ws && K % 8 == 0, "conv2d_fprop_stats: needs a statistics workspace and K %% 8 == 0");
+  B200_REQUIRE(stats_ws_bytes >= b200_bn_workspace_bytes(0, K), "conv2d_fprop_stats: statistics workspace too small");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(stats_ws) & 7) == 0, "conv2d_fprop_stats: statistics workspace must be 8-byte aligned");
+  bool fused = false;
+  if (int rc = conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
+                                 ws_bytes, stream, reinterpret_cast<double*>(stats_ws), &fused))
+    return rc;
+  if (fused) return 0;
+  // kernels without the fused epilogue (direct, single-CTA): one accumulate-only pass over y
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  return bn_sums_launch(y, (int64_t)N * P * Q, K, stats_ws, stats_ws_bytes, 0, 0.f, 0.f, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, as_stream(stream));
 }
 
 // merge of the parity-split dx with an optional addend
@@ -1066,13 +1123,11 @@ extern "C" size_t b200_bn_workspace_bytes(int64_t rows, int C) {
   return (size_t)BN_SLOTS * bn_slot_stride(C) * sizeof(double) + 16;
 }
 
-extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum,
-                             float* mean, float* invstd, float* running_mean, float* running_var,
-                             int64_t* num_batches_tracked, void* ws, size_t ws_bytes,
-                             b200_stream_t stream) {
-  B200_REQUIRE(x && mean && invstd && ws, "bn_stats: null pointer");
+static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t ws_bytes, int finalize,
+                          float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, cudaStream_t st) {
   B200_REQUIRE(C % 8 == 0, "bn_stats: C=%d must be a multiple of 8", C);
-  B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_stats: workspace too small");
+  B200_REQUIRE(ws && ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_stats: workspace too small");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_stats: workspace must be 8-byte aligned");
   static const int bps = std::max(1, env_int("B200_BN_STATS_BPS", 4));
   BnStatsArgs a;
@@ -1081,10 +1136,38 @@ extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, floa
   a.num_batches_tracked = num_batches_tracked;
   a.accum = reinterpret_cast<double*>(ws);
   a.ticket = reinterpret_cast<unsigned int*>(a.accum + BN_SLOTS * bn_slot_stride(C));
+  a.finalize = finalize;
   const int CG = C / 8;
   dim3 grid(bn_blocks(rows, C, bps, 8), (CG + EW_THREADS - 1) / EW_THREADS);
-  launch_k(bn_stats_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), as_stream(stream), a);
+  launch_k(bn_stats_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a);
   B200_LAUNCH_CHECK("bn_stats_kernel");
+  return 0;
+}
+
+extern "C" int b200_bn_stats(const void* x, int64_t rows, int C, float eps, float momentum,
+                             float* mean, float* invstd, float* running_mean, float* running_var,
+                             int64_t* num_batches_tracked, void* ws, size_t ws_bytes,
+                             b200_stream_t stream) {
+  B200_REQUIRE(x && mean && invstd && ws, "bn_stats: null pointer");
+  return bn_sums_launch(x, rows, C, ws, ws_bytes, 1, eps, momentum, mean, invstd, running_mean,
+                        running_var, num_batches_tracked, as_stream(stream));
+}
+
+extern "C" int b200_bn_stats_finalize(int64_t rows, int C, float eps, float momentum, float* mean,
+                                      float* invstd, float* running_mean, float* running_var,
+                                      int64_t* num_batches_tracked, void* ws, size_t ws_bytes,
+                                      b200_stream_t stream) {
+  B200_REQUIRE(mean && invstd && ws && rows > 0, "bn_stats_finalize: bad arguments");
+  B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_stats_finalize: workspace too small");
+  BnStatsArgs a;
+  a.x = nullptr; a.rows = rows; a.C = C; a.eps = eps; a.momentum = momentum;
+  a.mean = mean; a.invstd = invstd; a.running_mean = running_mean; a.running_var = running_var;
+  a.num_batches_tracked = num_batches_tracked;
+  a.accum = reinterpret_cast<double*>(ws);
+  a.ticket = nullptr;
+  a.finalize = 1;
+  launch_k(bn_stats_finalize_kernel, (unsigned)((C + 255) / 256), 256, 0, as_stream(stream), a);
+  B200_LAUNCH_CHECK("bn_stats_finalize_kernel");
   return 0;
 }
 

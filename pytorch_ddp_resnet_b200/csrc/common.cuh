@@ -113,6 +113,19 @@ __device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const uint64_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// BN accumulator workspace layout (shared by the BN kernels and the conv epilogues)
+// ---------------------------------------------------------------------------------------------
+// Accumulator workspace of the reduction kernels: BN_SLOTS copies of fp64 [2][C], `slot_stride` doubles
+// apart (>= 4 KB so the copies land in different L2 slices), followed by the ticket counter. Block b adds
+// into copy b % BN_SLOTS: ncu showed ~600 blocks firing their atomics at the same few hundred addresses
+// in one burst took as long as the streaming loop itself (same-address atomics serialise in one slice).
+constexpr int BN_SLOTS = 8;
+__host__ __device__ __forceinline__ size_t bn_slot_stride(int C) {
+  const size_t need = 2 * (size_t)C;              // doubles
+  return (need < 512 ? 512 : (need + 31) / 32 * 32) + 32;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -55,7 +55,60 @@ struct ConvTcArgs {
   bf16* out;
   const bf16* residual;
   const float* bias;
+  double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
 };
+
+// -------------------------------------------------------------------------------------------------
+// Fused batch-norm statistics of a conv output (epilogue side, STATS = true instantiations).
+// The BN that follows a conv needs sum(y) and sum(y^2) per output channel over all pixels; computing
+// them here saves the separate statistics kernel (one more pass over y and ~12 us of launch / drain
+// per BN layer). Per 16-column chunk each epilogue warp transposes-and-reduces its 32 rows with 32
+// shuffles (lane L ends with column L >> 1: sum in even lanes, sum of squares in odd lanes) and adds
+// them to the CTA's shared partials; per tile the 4 epilogue warps flush those with one fp64 atomic per
+// (channel, statistic) into slot (tile % BN_SLOTS) of the accumulator workspace (common.cuh).
+// -------------------------------------------------------------------------------------------------
+constexpr int EPI_STATS_MAX_BN = 256;
+
+__device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float* s_part, int c) {
+  float s[16], q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    s[j] = fr[j];
+    q[j] = fr[j] * fr[j];
+  }
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step;  // partner distance 16, 8, 4, 2
+    const int w = 8 >> step;     // values kept 8, 4, 2, 1
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float rs = __shfl_xor_sync(0xffffffffu, up ? s[i] : s[i + w], off);
+      const float rq = __shfl_xor_sync(0xffffffffu, up ? q[i] : q[i + w], off);
+      s[i] = (up ? s[i + w] : s[i]) + rs;
+      q[i] = (up ? q[i + w] : q[i]) + rq;
+    }
+  }
+  const float s0 = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
+  const float q0 = q[0] + __shfl_xor_sync(0xffffffffu, q[0], 1);
+  atomicAdd(&s_part[(c + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? q0 : s0);
+}
+
+// barrier among the 128 epilogue threads of a CTA (warps 2..5), id 1 (id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// after the last chunk of a tile: flush the CTA's partials of output-channel tile `nt`
+__device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, int C, int BN, int nt,
+                                                int slot, int m) {
+  epi_bar();
+  double* dst = accum + (size_t)(slot % BN_SLOTS) * bn_slot_stride(C) + (size_t)nt * BN;
+  for (int i = m; i < 2 * BN; i += 128) {
+    const float v = s_part[i];
+    s_part[i] = 0.f;
+    atomicAdd(dst + (size_t)(i & 1) * C + (i >> 1), (double)v);
+  }
+  epi_bar();
+}
 
 template <int KC>
 struct KMajorCfg {
@@ -272,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   are local in each CTA and signalled by the leader's multicast tcgen05.commit; tempty[a] lives in the
 //   leader and collects the 8 epilogue warps of the pair.
 // -------------------------------------------------------------------------------------------------
-template <int KC>
+template <int KC, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvTcArgs args) {
@@ -282,6 +335,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_BN : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -408,6 +462,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ni = m / (args.bw * args.bh);
     int as = 0;
     uint32_t aph = 0;
+    if (STATS) {
+      for (int i = m; i < 2 * EPI_STATS_MAX_BN; i += 128) s_part[i] = 0.f;
+      epi_bar();
+    }
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
       const int mt = (ct / args.n_ntiles) * 2 + crank;
@@ -428,8 +486,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
         if (valid) {
-          float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
           if (brow) {
@@ -446,16 +506,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
           }
+          if (STATS) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]);  // statistics of the values stored
+          }
           Vec8 o0, o1;
           o0.from_float(f);
           o1.from_float(f + 8);
           *reinterpret_cast<uint4*>(orow + c) = o0.raw;
           *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
         }
+        if (STATS) epi_stats_chunk(f, lane, s_part, c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, m);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -499,13 +565,14 @@ struct ConvHaloArgs {
   bf16* out;
   const bf16* residual;
   const float* bias;
+  double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
 };
 
 // MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
 // buffered when MT = 2, epilogue with 4 warps PER TILE). ncu on MT = 1: 330 MB per launch through the
 // L2->SM path, 236 MB of it the same filter tiles fetched once per tile pair; MT = 2 halves that but was
 // measured SLOWER (983 vs 1183 TFLOP/s at 160 channels): kept for experiments, default MT = 1.
-template <int KC, int MT>
+template <int KC, int MT, bool STATS>
 __global__ void __launch_bounds__(64 + 128 * MT, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvHaloArgs args) {
@@ -515,6 +582,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t bfull_bar[HALO_BSTAGES_MAX], bempty_bar[HALO_BSTAGES_MAX];
   __shared__ uint64_t tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_BN : 1];
+  static_assert(!STATS || MT == 1, "fused statistics: one pixel tile per CTA");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -662,6 +731,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int hi = m >> 3;
     int as = 0;
     uint32_t aph = 0;
+    if (STATS) {
+      for (int i = m; i < 2 * EPI_STATS_MAX_BN; i += 128) s_part[i] = 0.f;
+      epi_bar();
+    }
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
       const int mt = ((ct / args.n_ntiles) * 2 + crank) * MT + t;
@@ -699,15 +772,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
         }
+        if (STATS) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]);  // statistics of the values stored
+        }
         Vec8 o0, o1;
         o0.from_float(f);
         o1.from_float(f + 8);
         *reinterpret_cast<uint4*>(orow + c) = o0.raw;
         *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+        if (STATS) epi_stats_chunk(f, lane, s_part, c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, m);
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
   }

@@ -31,16 +31,6 @@ __device__ __forceinline__ void dropout8(float* f, uint64_t seed, size_t v, uint
 // the whole kernel) and a row lane `rl`; acc[] holds NACC*8 per-channel partial sums of that thread.
 // The block reduces over row lanes and writes partial[blockIdx.x][a][C] for a < NACC.
 // -------------------------------------------------------------------------------------------------
-// Accumulator workspace of the reduction kernels: BN_SLOTS copies of fp64 [2][C], `slot_stride` doubles
-// apart (>= 4 KB so the copies land in different L2 slices), followed by the ticket counter. Block b adds
-// into copy b % BN_SLOTS: ncu showed ~600 blocks firing their atomics at the same few hundred addresses
-// in one burst took as long as the streaming loop itself (same-address atomics serialise in one slice).
-constexpr int BN_SLOTS = 8;
-__host__ __device__ __forceinline__ size_t bn_slot_stride(int C) {
-  const size_t need = 2 * (size_t)C;              // doubles
-  return (need < 512 ? 512 : (need + 31) / 32 * 32) + 32;
-}
-
 template <int NACC>
 __device__ __forceinline__ void block_channel_reduce(const float* acc, float* smem, int cgl, int rl,
                                                      int CGb, int RP, bool active, double* accum,
@@ -126,7 +116,24 @@ struct BnStatsArgs {
   int64_t* num_batches_tracked;
   double* accum;          // BN_SLOTS x [2][C], zero on entry, zero again on exit
   unsigned int* ticket;   // zero on entry, zero again on exit
+  int finalize;           // 0: accumulate only (the sums are finalized by bn_stats_finalize_kernel)
 };
+
+// one channel: drain the accumulator slots, write mean / invstd, update the running statistics
+__device__ __forceinline__ void bn_finalize_channel(const BnStatsArgs& a, int c) {
+  const int C = a.C;
+  const double s = drain_slots(a.accum, C, 0, c), ss = drain_slots(a.accum, C, 1, c);
+  const double m = s / (double)a.rows;
+  double var = ss / (double)a.rows - m * m;
+  if (var < 0.0) var = 0.0;
+  a.mean[c] = (float)m;
+  a.invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
+  if (a.running_mean) {
+    const double unbiased = a.rows > 1 ? var * (double)a.rows / (double)(a.rows - 1) : var;
+    a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)m;
+    a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
+  }
+}
 
 // Batch statistics in ONE launch: every block adds its per-channel sum / sum of squares to the fp64
 // accumulators; the block that finishes last turns them into mean / invstd / running statistics and
@@ -166,24 +173,19 @@ __global__ void __launch_bounds__(EW_THREADS, 4) bn_stats_kernel(const BnStatsAr
     }
   }
   block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, a.accum, C, g.cg0 * 8);
-  if (!last_block_done(a.ticket)) return;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double s = drain_slots(a.accum, C, 0, c), ss = drain_slots(a.accum, C, 1, c);
-    const double m = s / (double)a.rows;
-    double var = ss / (double)a.rows - m * m;
-    if (var < 0.0) var = 0.0;
-    a.mean[c] = (float)m;
-    a.invstd[c] = (float)(1.0 / sqrt(var + (double)a.eps));
-    if (a.running_mean) {
-      const double unbiased = a.rows > 1 ? var * (double)a.rows / (double)(a.rows - 1) : var;
-      a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)m;
-      a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
-    }
-  }
+  if (!a.finalize || !last_block_done(a.ticket)) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bn_finalize_channel(a, c);
   if (threadIdx.x == 0) {
     *a.ticket = 0u;
     if (a.num_batches_tracked) *a.num_batches_tracked += 1;
   }
+}
+
+// sums accumulated by a conv epilogue (or an accumulate-only pass) -> mean / invstd / running statistics
+__global__ void bn_stats_finalize_kernel(const BnStatsArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.C) bn_finalize_channel(a, c);
+  if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -48,6 +48,26 @@ def bn_accumulators(device: torch.device, nbytes: int = 0) -> torch.Tensor:
     return t
 
 
+# Fused conv + BN statistics: conv_fprop(want_stats=True) leaves the per-channel sums of its output in the
+# accumulators and records (output pointer, rows, C) here; the bn_stats call that follows on the SAME tensor
+# only finalizes them. Anything else that needs the accumulators first clears an unconsumed record.
+_pending_stats = {}
+
+
+def _accum_key(device: torch.device):
+    return (device.index, "capture" if torch.cuda.is_current_stream_capturing() else _stream())
+
+
+def _drop_pending_stats(device: torch.device) -> None:
+    rec = _pending_stats.pop(_accum_key(device), None)
+    if rec is not None:
+        rec[3].zero_()   # sums nobody consumed (e.g. a conv that is not followed by a batch norm)
+
+
+def fused_bn_stats_enabled() -> bool:
+    return os.environ.get("B200_FUSED_BN_STATS", "1") != "0"
+
+
 def tick(device: torch.device) -> None:
     _lib.require_device(device.index or 0)
     _lib.call("b200_tick", step_counter(device).data_ptr(), _stream())
@@ -128,7 +148,9 @@ def _out_hw(H, W, R, S, stride, pad):
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
 
 
-def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=None):
+def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=None,
+               want_stats: bool = False):
+    """want_stats: also accumulate the batch-norm sums of the output (consumed by the next bn_stats(y))."""
     _check_act(x, "conv_fprop.x")
     N, H, W, C = x.shape
     K, R, S, Cw = w_krsc.shape
@@ -141,6 +163,15 @@ def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=
     algo = conv_algo() if algo is None else algo
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_FPROP, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(x.device, nws) if nws else None
+    if want_stats and K % 8 == 0 and fused_bn_stats_enabled():
+        _drop_pending_stats(x.device)
+        nacc = _lib.load().b200_bn_workspace_bytes(N * P * Q, K)
+        acc = bn_accumulators(x.device, nacc)
+        _lib.call("b200_conv2d_fprop_stats", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
+                  y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, acc.data_ptr(),
+                  acc.numel() * 8, _stream())
+        _pending_stats[_accum_key(x.device)] = (y.data_ptr(), N * P * Q, K, acc)
+        return y
     _lib.call("b200_conv2d_fprop", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
               y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
     return y
@@ -254,6 +285,14 @@ def bn_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_va
     mean = torch.empty((C,), dtype=torch.float32, device=x.device)
     invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
     nws = _lib.load().b200_bn_workspace_bytes(rows, C)
+    rec = _pending_stats.pop(_accum_key(x.device), None)
+    if rec is not None:
+        if rec[:3] == (x.data_ptr(), rows, C):   # the conv that produced x already summed it
+            _lib.call("b200_bn_stats_finalize", rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
+                      _p(running_mean), _p(running_var), _p(num_batches_tracked), rec[3].data_ptr(),
+                      rec[3].numel() * 8, _stream())
+            return mean, invstd
+        rec[3].zero_()
     ws = bn_accumulators(x.device, nws)
     _lib.call("b200_bn_stats", x.data_ptr(), rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
               _p(running_mean), _p(running_var), _p(num_batches_tracked), ws.data_ptr(), nws, _stream())
@@ -293,6 +332,8 @@ def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = Tru
     dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
     dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
     nws = _lib.load().b200_bn_workspace_bytes(rows, C) if affine else 0
+    if affine:
+        _drop_pending_stats(dy.device)
     ws = bn_accumulators(dy.device, nws) if affine else None
     if addend is not None:
         _check_act(addend, "bn_act_bwd.addend")

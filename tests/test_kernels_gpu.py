@@ -140,6 +140,59 @@ def test_stem_conv_few_input_channels(geom, algo):
     assert rel_l2(db, dy.float().sum((0, 1, 2))) < 1e-3
 
 
+@pytest.mark.parametrize("algo", ["tc", "direct"])
+@pytest.mark.parametrize("shape", CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("with_residual", [False, True])
+def test_conv_fprop_fused_bn_statistics(shape, algo, with_residual):
+    """conv_fprop(want_stats=True) + bn_stats(y) (finalize only) == conv_fprop + the stand-alone bn_stats,
+    for the epilogue-fused kernels (SM pair, halo) and for the accumulate-only fallback (direct)."""
+    ops, _lib = _ops()
+    N, H, W, C, K, R, stride, pad = shape
+    if K % 8:
+        pytest.skip("statistics need K % 8 == 0")
+    a = {"tc": _lib.ALGO_TC, "direct": _lib.ALGO_DIRECT}[algo]
+    if algo == "tc" and not _lib.load().b200_conv2d_tc_supported(_lib.PASS_FPROP, N, H, W, C, K, R, R, stride, pad):
+        pytest.skip("shape not on the tcgen05 path")
+    x, w, dy = _conv_inputs(*shape)
+    res = dy if with_residual else None
+    rm, rv = torch.zeros(K, device="cuda"), torch.ones(K, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    y = ops.conv_fprop(x, w, stride, pad, residual=res, algo=a, want_stats=True)
+    mean, invstd = ops.bn_stats(y, 1e-5, 0.1, rm, rv, nbt)          # consumes the fused sums
+    y2 = ops.conv_fprop(x, w, stride, pad, residual=res, algo=a)
+    rm2, rv2 = torch.zeros(K, device="cuda"), torch.ones(K, device="cuda")
+    mean2, invstd2 = ops.bn_stats(y2, 1e-5, 0.1, rm2, rv2, None)    # stand-alone kernel
+    assert torch.equal(y, y2)
+    yf = y.float().reshape(-1, K)
+    assert (mean - yf.mean(0)).abs().max().item() <= 1e-5 + 1e-4 * yf.abs().mean().item()
+    assert rel_l2(mean, mean2) <= 1e-5 or (mean - mean2).abs().max().item() <= 1e-6
+    assert rel_l2(invstd, invstd2) <= 1e-5
+    assert rel_l2(rm, rm2) <= 1e-5 or (rm - rm2).abs().max().item() <= 1e-6
+    assert rel_l2(rv, rv2) <= 1e-5
+    assert nbt.item() == 1
+    # the accumulators are clean again: an unrelated statistics call is unaffected
+    z = torch.randn(64, K, device="cuda").bfloat16()
+    m3, _ = ops.bn_stats(z, 1e-5)
+    assert (m3 - z.float().mean(0)).abs().max().item() <= 1e-5
+
+
+def test_unconsumed_fused_statistics_are_discarded():
+    """A conv that summed its statistics but is NOT followed by bn_stats on its output must not leak
+    those sums into the next user of the accumulators."""
+    ops, _lib = _ops()
+    x, w, dy = _conv_inputs(4, 16, 16, 64, 64, 3, 1, 1)
+    ops.conv_fprop(x, w, 1, 1, want_stats=True)
+    z = torch.randn(4, 16, 16, 64, device="cuda").bfloat16()
+    m, istd = ops.bn_stats(z, 1e-5)
+    zf = z.float().reshape(-1, 64)
+    assert (m - zf.mean(0)).abs().max().item() <= 1e-5
+    assert rel_l2(istd, (zf.var(0, unbiased=False) + 1e-5).rsqrt()) <= 1e-4
+    ops.conv_fprop(x, w, 1, 1, want_stats=True)
+    g = ops.bn_act_bwd(dy, None, z, m, istd, torch.ones(64, device="cuda"), relu=False)
+    gref = dy.float().reshape(-1, 64).sum(0)
+    assert rel_l2(g[2], gref) <= 1e-4
+
+
 def test_weight_prep():
     ops, _ = _ops()
     w = torch.randn(48, 3, 3, 40, device="cuda")
