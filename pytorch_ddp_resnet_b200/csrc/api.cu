@@ -375,7 +375,7 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
   const int grid = std::min(num_ptiles, num_sms() / 2) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TC2_THREADS);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -449,7 +449,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   const int grid = std::min(num_units, num_sms() / 2) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(64 + 128 * MT);
+  cfg.blockDim = dim3(TC2_THREADS);
   cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -23,6 +23,10 @@ namespace b200 {
 constexpr int TC_MAX_TAPS = 9;
 constexpr int TC_MAX_STAGES = 20;
 constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+// SM-pair conv kernels: 8 epilogue warps, two per TMEM lane quadrant, each draining half of the
+// accumulator columns (ncu: with 4 warps the epilogue of a 160-channel tile was as long as its MMAs)
+constexpr int TC2_THREADS = 64 + 256;
+constexpr int TC2_EPI_THREADS = 256;
 
 struct TapTable {
   int n;
@@ -94,15 +98,15 @@ __device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float
   atomicAdd(&s_part[(c + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? q0 : s0);
 }
 
-// barrier among the 128 epilogue threads of a CTA (warps 2..5), id 1 (id 0 is __syncthreads)
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// barrier among the 256 epilogue threads of a CTA (warps 2..9), id 1 (id 0 is __syncthreads)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // after the last chunk of a tile: flush the CTA's partials of output-channel tile `nt`
 __device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, int C, int BN, int nt,
-                                                int slot, int m) {
+                                                int slot, int e) {
   epi_bar();
   double* dst = accum + (size_t)(slot % BN_SLOTS) * bn_slot_stride(C) + (size_t)nt * BN;
-  for (int i = m; i < 2 * BN; i += 128) {
+  for (int i = e; i < 2 * BN; i += TC2_EPI_THREADS) {
     const float v = s_part[i];
     s_part[i] = 0.f;
     atomicAdd(dst + (size_t)(i & 1) * C + (i >> 1), (double)v);
@@ -326,7 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   leader and collects the 8 epilogue warps of the pair.
 // -------------------------------------------------------------------------------------------------
 template <int KC, bool STATS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvTcArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -353,8 +357,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 8);
-    mbar_init(&tempty_bar[1], 8);
+    mbar_init(&tempty_bar[0], 16);
+    mbar_init(&tempty_bar[1], 16);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -455,7 +459,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (both CTAs, own TMEM, own pixel tile) =====================
-    const int wq = warp & 3;
+    const int wq = warp & 3;                       // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;              // which half of the columns it drains
+    const int e = (warp - 2) * 32 + lane;          // index among the epilogue threads
+    const int c_lo = half * (args.BN >> 1), c_hi = c_lo + (args.BN >> 1);
     const int m = wq * 32 + lane;
     const int wi = m % args.bw;
     const int hi = (m / args.bw) % args.bh;
@@ -463,7 +470,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int as = 0;
     uint32_t aph = 0;
     if (STATS) {
-      for (int i = m; i < 2 * EPI_STATS_MAX_BN; i += 128) s_part[i] = 0.f;
+      for (int i = e; i < 2 * EPI_STATS_MAX_BN; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
@@ -482,7 +489,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
-      for (int c = 0; c < args.BN; c += 16) {
+      for (int c = c_lo; c < c_hi; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -521,7 +528,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
-      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, m);
+      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, e);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -573,7 +580,7 @@ struct ConvHaloArgs {
 // L2->SM path, 236 MB of it the same filter tiles fetched once per tile pair; MT = 2 halves that but was
 // measured SLOWER (983 vs 1183 TFLOP/s at 160 channels): kept for experiments, default MT = 1.
 template <int KC, int MT, bool STATS>
-__global__ void __launch_bounds__(64 + 128 * MT, 1)
+__global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvHaloArgs args) {
   constexpr int NBUF = (MT == 1) ? 2 : 1;   // accumulator sets
@@ -601,7 +608,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&pfull_bar[i], 1);
       mbar_init(&pempty_bar[i], 1);
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8 * MT);
+      mbar_init(&tempty_bar[i], 16);
     }
     for (int i = 0; i < args.bstages; ++i) {
       mbar_init(&bfull_bar[i], 1);
@@ -724,15 +731,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================== epilogue (both CTAs, own TMEM): 4 warps per pixel tile =====================
+    // 8 epilogue warps: MT = 1 -> two warps per quadrant, each draining half of the columns;
+    //                   MT = 2 -> four warps per pixel tile
     const int wq = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int t = (warp - 2) >> 2;           // pixel tile of this CTA handled by this warp
+    const int grp = (warp - 2) >> 2;
+    const int t = (MT == 2) ? grp : 0;       // pixel tile of this CTA handled by this warp
+    const int e = (warp - 2) * 32 + lane;    // index among the epilogue threads
+    const int cw = (MT == 2) ? args.BN : (args.BN >> 1);
+    const int c_lo = (MT == 2) ? 0 : grp * cw, c_hi = c_lo + cw;
     const int m = wq * 32 + lane;
     const int wi = m & 7;
     const int hi = m >> 3;
     int as = 0;
     uint32_t aph = 0;
     if (STATS) {
-      for (int i = m; i < 2 * EPI_STATS_MAX_BN; i += 128) s_part[i] = 0.f;
+      for (int i = e; i < 2 * EPI_STATS_MAX_BN; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
@@ -751,7 +764,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u + (uint32_t)(t * args.BN);
-      for (int c = 0; c < args.BN; c += 16) {
+      for (int c = c_lo; c < c_hi; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -786,7 +799,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
-      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, m);
+      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, e);
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
   }
