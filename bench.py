@@ -8,8 +8,8 @@ bf16, N GPUs of one node (BASELINE.json configs[1]; N > 1 is the DDP weak-scalin
            --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's algorithm on the host CPU cores
 
-One "step" = forward + mean cross-entropy + backward (+ bucketed NCCL gradient all-reduce through
-DistributedDataParallel) + fused SGD update through the public API of pytorch_ddp_resnet_b200.
+One "step" = forward + mean cross-entropy + backward (+ the NCCL gradient all-reduce of the data-parallel
+ranks) + fused SGD update through the public API of pytorch_ddp_resnet_b200.
 `value`  : images/s with the batch already resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : the same step fed from pinned host memory (H2D copy of x, y every step) with a device->host
            read of the loss every step, inside the timed region.
@@ -37,7 +37,7 @@ SGD = dict(lr=0.1, momentum=0.9, dampening=0.0, nesterov=True, weight_decay=5e-4
 WORKLOAD = "WRN-28-10 (dropout 0.3) CIFAR-10-shape 32x32 synthetic bf16 training, batch 128/GPU"
 METRIC = "train img/s WRN-28-10 CIFAR"
 # DRAM bytes per launch of the dominant kernel from the round's `ncu --set full` capture (profiles/)
-DOMINANT_KERNEL_DRAM_BYTES = 44.27e6
+DOMINANT_KERNEL_DRAM_BYTES = 44.25e6
 
 
 def peaks():
@@ -325,9 +325,10 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16"], "traffic": DOMINANT_KERNEL_DRAM_BYTES,
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                       "(profiles/r01_conv_ncu_metrics.txt); algorithmic bytes 84.3e6",
-                     "kernel": "conv_tc2_kernel<32> (cta_group::2) fprop 3x3 s1 160->160 @32x32 batch 128 "
-                               "(60.4 GFLOP/launch)",
+                                       "(profiles/r01_final_ncu_metrics.txt: 42.44 MB read + 1.82 MB written); "
+                                       "algorithmic bytes 84.3e6 (the output is still in L2 at kernel end)",
+                     "kernel": "conv_tc2h_kernel<32,1,false> (cta_group::2, halo reuse) fprop 3x3 s1 160->160 "
+                               "@32x32 batch 128 (60.4 GFLOP/launch)",
                      "kernel_ms": kms, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                      "step_conv_tflops": conv_tflops_in_step,
                      "step_conv_frac_of_sustained": conv_tflops_in_step / pk["bf16_sustained"]},
