@@ -47,11 +47,17 @@ def _worker(rank, world, port, use_graph):
     local = ResNet(SPEC, True, True, 0.0).cuda().train()
     local.load_state_dict(init)
     compute_losses_and_metrics(logits=local(x), labels=y)["loss"].backward()
+    means = {}
     for n, p in local.named_parameters():
         gmean = p.grad.clone()
         dist.all_reduce(gmean)
-        gmean /= world
-        err = ((ddp_grads[n] - gmean).norm() / gmean.norm().clamp_min(1e-12)).item()
+        means[n] = gmean / world
+    # Gradients whose true value is zero (the bias of a conv that feeds a batch norm) are pure rounding
+    # noise, and the atomics in the statistics / wgrad kernels make the last bits run-dependent: errors
+    # are measured against the larger of the gradient's own norm and 1 % of the largest gradient norm.
+    scale = max(g.norm().item() for g in means.values())
+    for n, gmean in means.items():
+        err = ((ddp_grads[n] - gmean).norm() / gmean.norm().clamp_min(1e-2 * scale)).item()
         assert err < 1e-3, (n, err)
 
     # (2) replicas stay identical through optimizer steps (eager or whole-step CUDA graph)
