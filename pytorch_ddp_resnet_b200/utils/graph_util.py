@@ -1,6 +1,6 @@
 """
-Whole-step CUDA-graph capture: forward + loss/metrics + backward (+ DDP's bucketed NCCL all-reduce)
-+ fused SGD update become ONE graph launch per step, removing ~300 host-side kernel launches.
+Whole-step CUDA-graph capture: forward + loss/metrics + backward + fused SGD update become ONE graph
+launch per step, removing ~200 host-side kernel launches (data parallel: see below).
 
 The training step of the reference (resnet/algos/training.py:94-113) is host-driven op by op; on a
 B200 the WRN-28-10 step is a few milliseconds of GPU time, less than the Python time needed to
@@ -19,8 +19,8 @@ What keeps a replay equal to an eager step:
 Inputs must keep the captured shape; other shapes (e.g. a ragged last batch) run eagerly.
 
 Data parallel (classifier is a DistributedDataParallel wrapper): the graph holds forward + backward of
-the LOCAL module (no DDP hooks run inside a capture); each replay is followed by ONE coalesced NCCL
-all-reduce (average) over the static gradient buffers and the fused SGD launch. BatchNorm buffers stay
+the LOCAL module (no DDP hooks run inside a capture); each replay is followed by ONE NCCL
+all-reduce (average) of the flat gradient buffer and the fused SGD launch. BatchNorm buffers stay
 per-rank during graphed training and are re-synchronised from rank 0 whenever the DDP wrapper runs a
 forward (evaluation, eager steps), which is where the reference's per-forward broadcast is observable.
 """
