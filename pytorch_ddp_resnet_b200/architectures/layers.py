@@ -92,8 +92,10 @@ class Conv2d(tc.nn.Module):
         else:
             self.register_parameter("bias", None)
         self._cache = None
-        # optional fp32 [K,R,S,C] destination for the weight gradient (a view into a flat all-reduce buffer)
+        # optional destinations of the gradients (views into the flat buffer of utils/graph_util.py's
+        # bucketed all-reduce): fp32 [K,R,S,C] for the filter, fp32 [K] for the bias
         self.grad_out = None
+        self.bias_grad_out = None
 
     def _apply(self, fn, recurse=True):
         # keep the KRSC physical layout across .to()/.cuda()/.float() (1x1 filters are ambiguous)
@@ -103,6 +105,10 @@ class Conv2d(tc.nn.Module):
             w.data = w.data.contiguous(memory_format=torch.channels_last)
         self._cache = None
         return self
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
+                f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
 
     def krsc(self) -> torch.Tensor:
         """fp32 [K, R, S, C] view of the master weight."""
@@ -160,10 +166,6 @@ class WeightPrepPlan:
         for c, k, (_, wk, wt) in zip(convs, keys, self.entries):
             c._cache = (k, wk, wt)
 
-    def extra_repr(self):
-        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
-                f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
-
 
 def conv_weight_grad(dw_krsc: torch.Tensor) -> torch.Tensor:
     """fp32 [K,R,S,C] kernel output -> gradient shaped like the [O,I,kh,kw] channels_last parameter
@@ -186,6 +188,10 @@ class BatchNorm2d(tc.nn.Module):
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.grad_out = None   # optional (dgamma, dbeta) fp32 [C] destinations in a flat gradient buffer
+
+    def grad_dst(self):
+        return dict(out_dgamma=self.grad_out[0], out_dbeta=self.grad_out[1]) if self.grad_out else {}
 
     def batch_stats(self, x_nhwc):
         """Training statistics of x (+ in-place running-stat update)."""
@@ -224,9 +230,10 @@ class Linear(tc.nn.Module):
         tc.nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
         bound = 1.0 / math.sqrt(in_features)
         tc.nn.init.uniform_(self.bias, -bound, bound)
+        self.grad_out = None   # optional (dw [O,I], db [O]) destinations in a flat gradient buffer
 
     def forward(self, x):
-        return LinearFn.apply(x, self.weight, self.bias)
+        return LinearFn.apply(x, self.weight, self.bias, self)
 
     def extra_repr(self):
         return f"{self.in_features}, {self.out_features}"
@@ -275,7 +282,7 @@ class TopConvFn(torch.autograd.Function):
         g = grad_nhwc(gy)
         k = mod.kernel_size
         dw, db = ops.conv_wgrad(g, xh, k, k, mod.stride, mod.padding, want_dbias=mod.bias is not None,
-                                out=mod.grad_out)
+                                out=mod.grad_out, out_db=mod.bias_grad_out)
         dx = None
         if ctx.need_dx:
             d = ops.conv_dgrad(g, wt, (xh.shape[1], xh.shape[2]), mod.stride, mod.padding)
@@ -299,6 +306,7 @@ class BnActFn(torch.autograd.Function):
             mean, invstd = bn.batch_stats(xh)
             y = ops.bn_act_fwd(xh, mean, invstd, gamma, beta, relu=relu)
             ctx.save_for_backward(xh, y, mean, invstd, gamma)
+            ctx.bn = bn
         else:
             y = ops.bn_act_fwd(xh, bn.running_mean, bn.running_var, gamma, beta, stat_is_var=True,
                                eps=bn.eps, relu=relu)
@@ -314,7 +322,8 @@ class BnActFn(torch.autograd.Function):
         if not ctx.train:
             raise B200Error("backward through eval-mode BatchNorm is not supported")
         xh, y, mean, invstd, gamma = ctx.saved_tensors
-        dx, dgamma, dbeta, _ = ops.bn_act_bwd(g, y, xh, mean, invstd, gamma, relu=ctx.relu)
+        dx, dgamma, dbeta, _ = ops.bn_act_bwd(g, y, xh, mean, invstd, gamma, relu=ctx.relu,
+                                              **ctx.bn.grad_dst())
         return as_nchw_view(dx), dgamma, dbeta, None, None
 
 
@@ -344,11 +353,12 @@ class LinearFn(torch.autograd.Function):
     """`fI,O` token after Flatten (resnet.py:117-120): bf16 logits, fp32 parameter gradients."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, mod=None):
         if not x.is_cuda:
             raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         x2 = x if (x.dtype == torch.bfloat16 and x.is_contiguous()) else x.to(torch.bfloat16).contiguous()
         y = ops.linear_fwd(x2, weight, bias)
+        ctx.mod = mod
         ctx.need_dx = x.requires_grad
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(x2, weight)
@@ -358,7 +368,8 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, gy):
         x2, weight = ctx.saved_tensors
         g = gy if (gy.dtype == torch.bfloat16 and gy.is_contiguous()) else gy.to(torch.bfloat16).contiguous()
-        dx, dw, db = ops.linear_bwd(g, x2, weight, want_dx=ctx.need_dx)
+        dst = ctx.mod.grad_out if (ctx.mod is not None and ctx.mod.grad_out) else (None, None)
+        dx, dw, db = ops.linear_bwd(g, x2, weight, want_dx=ctx.need_dx, out_dw=dst[0], out_db=dst[1])
         if dx is not None and ctx.x_dtype != torch.bfloat16:
             dx = dx.to(ctx.x_dtype)
-        return dx, dw, db
+        return dx, dw, db, None

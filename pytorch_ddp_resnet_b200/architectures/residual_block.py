@@ -114,6 +114,7 @@ class _BlockFn(torch.autograd.Function):
         if not ctx.training:
             raise B200Error("backward through an eval-mode block is not supported (BN uses running stats)")
         convs: List[Conv2d] = block._convs()
+        norms: List[BatchNorm2d] = block._norms()
         n = len(convs)
         p, seeds = ctx.p, ctx.seeds
         identity = not block._downsample
@@ -136,14 +137,14 @@ class _BlockFn(torch.autograd.Function):
                 addend = dskip if (j == 0 and identity) else None
                 cur, dgs[j], dbs[j], _ = ops.bn_act_bwd(
                     da, a, hin, st["mean"], st["invstd"], st["gamma"], relu=True, dropout_p=p,
-                    seed=seeds[j], addend=addend)
+                    seed=seeds[j], addend=addend, **norms[j].grad_dst())
             dx = cur
         else:
             # last BN: relu(bn(c_n) + skip)
             st = ctx.stats[n - 1]
             cur, dgs[n - 1], dbs[n - 1], dskip = ops.bn_act_bwd(
                 g, ctx.saved_in[n - 1], ctx.saved_conv[n - 1], st["mean"], st["invstd"], st["gamma"],
-                relu=True, want_dskip=True)
+                relu=True, want_dskip=True, **norms[n - 1].grad_dst())
             for j in range(n - 1, -1, -1):
                 c = convs[j]
                 d = ctx.saved_act[j]
@@ -160,7 +161,7 @@ class _BlockFn(torch.autograd.Function):
                     st = ctx.stats[j - 1]
                     cur, dgs[j - 1], dbs[j - 1], _ = ops.bn_act_bwd(
                         dd, ctx.saved_in[j - 1], ctx.saved_conv[j - 1], st["mean"], st["invstd"],
-                        st["gamma"], relu=True)
+                        st["gamma"], relu=True, **norms[j - 1].grad_dst())
                 else:
                     cur = dd
             dx = cur

@@ -37,10 +37,10 @@ static int fail(int code, const char* fmt, ...) {
     if (!(cond)) return fail(1, __VA_ARGS__); \
   } while (0)
 
-#define B200_CUDA(call)                                                                  \
+#define B200_CUDA(...)                                                                   \
   do {                                                                                   \
-    cudaError_t e__ = (call);                                                            \
-    if (e__ != cudaSuccess) return fail(2, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    cudaError_t e__ = (__VA_ARGS__);                                                     \
+    if (e__ != cudaSuccess) return fail(2, "%s failed: %s", #__VA_ARGS__, cudaGetErrorString(e__)); \
   } while (0)
 
 static std::atomic<long long> g_launches{0};
@@ -74,14 +74,34 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// Per-device caches (one process may drive several GPUs): SM count, and "max dynamic shared memory
+// already raised for this kernel on this device".
+constexpr int MAX_DEVICES = 64;
+static int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+  return dev;
+}
+
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  static int n[MAX_DEVICES] = {0};
+  const int dev = cur_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+template <auto Kernel>
+static cudaError_t ensure_max_smem(int bytes) {
+  static bool done[MAX_DEVICES] = {false};
+  const int dev = cur_device();
+  if (done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
 }
 
 static inline int ew_grid(size_t work_items, int per_block = EW_THREADS) {
@@ -309,13 +329,8 @@ static int conv_cluster_size() {
 template <int KC, int CS>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                           cudaStream_t st) {
-  static bool attr_set = false;
   const int max_dyn = 228352;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_dyn));
-    attr_set = true;
-  }
+  B200_CUDA(ensure_max_smem<conv_tc_kernel<KC, CS>>(max_dyn));
   a.a_bytes = 128u * KC * 2u;
   const uint32_t b_bytes = ((uint32_t)a.BN * KC * 2u + 1023u) & ~1023u;
   a.stage_bytes = a.a_bytes + b_bytes;
@@ -347,13 +362,8 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
 template <int KC, bool STATS>
 static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                            cudaStream_t st) {
-  static bool attr_set = false;
   const int max_dyn = 228352;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KC, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_dyn));
-    attr_set = true;
-  }
+  B200_CUDA(ensure_max_smem<conv_tc2_kernel<KC, STATS>>(max_dyn));
   a.a_bytes = 128u * KC * 2u;
   const uint32_t b_bytes = ((uint32_t)(a.BN / 2) * KC * 2u + 1023u) & ~1023u;
   a.block_bytes = a.a_bytes + b_bytes;
@@ -406,13 +416,8 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
                             int wcols, const TapTable& taps, void* out, const void* residual,
                             const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
                             cudaStream_t st) {
-  static bool attr_set = false;
   const int max_dyn = 228352;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc2h_kernel<KC, MT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_dyn));
-    attr_set = true;
-  }
+  B200_CUDA(ensure_max_smem<conv_tc2h_kernel<KC, MT, STATS>>(max_dyn));
   ConvHaloArgs a;
   memset(&a, 0, sizeof(a));
   a.tiles_w = Q / 8; a.tiles_h = P / 16;
@@ -796,13 +801,8 @@ static int wgrad_mtiles_per_cta() {
 template <int SL, int CS, int MT>
 static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, WgradTcArgs& a,
                            cudaStream_t st) {
-  static bool attr_set = false;
   const int max_dyn = 228352;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<SL, CS, MT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-    attr_set = true;
-  }
+  B200_CUDA(ensure_max_smem<wgrad_tc_kernel<SL, CS, MT>>(max_dyn));
   a.stage_bytes = (uint32_t)(MT * (128 / SL) + a.nb) * a.slab_bytes;
   a.stages = std::min<int>(8, (max_dyn - 1024) / (int)a.stage_bytes);
   if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
@@ -912,12 +912,7 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles, 5);
   for (int t = 0; t < 9; ++t) a.wcol[t] = taps.wcol[t];
   a.dw = dw;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(wgrad_tc2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   max_dyn));
-    attr_set = true;
-  }
+  B200_CUDA(ensure_max_smem<wgrad_tc2h_kernel>(max_dyn));
   if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
   CUtensorMap tmX, tmDy;
   if (int rc = make_tmap_nhwc(&tmX, act, N, P, Q, C, 32, pw, bh, bn)) return rc;

@@ -92,6 +92,9 @@ def _check_act(t: torch.Tensor, name: str) -> None:
         raise _lib.B200Error(
             f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device} "
             f"contiguous={t.is_contiguous()}")
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.B200Error(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                             f"{torch.cuda.current_device()} (kernels launch on the current device's stream)")
     _lib.require_device(t.device.index or 0)
 
 
@@ -197,9 +200,9 @@ def conv_dgrad(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, addend
 
 
 def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = False, algo=None,
-               out=None):
-    """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None). `out`: optional preallocated dw (e.g. a view
-    into a flat gradient buffer that a single NCCL all-reduce covers)."""
+               out=None, out_db=None):
+    """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None). `out` / `out_db`: optional preallocated
+    destinations (views into the flat gradient buffer that the bucketed NCCL all-reduce covers)."""
     _check_act(dy, "conv_wgrad.dy")
     _check_act(x, "conv_wgrad.x")
     if _overlap["on"]:
@@ -208,7 +211,7 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
         _overlap["on"] = False
         try:
             with torch.cuda.stream(side):
-                res = conv_wgrad(dy, x, R, S, stride, pad, want_dbias, algo, out)
+                res = conv_wgrad(dy, x, R, S, stride, pad, want_dbias, algo, out, out_db)
         finally:
             _overlap["on"] = True
         _overlap["keep"][x.device.index].append((dy, x, res))
@@ -221,7 +224,9 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
         dw = out
     else:
         dw = torch.empty((K, R, S, C), dtype=torch.float32, device=x.device)
-    db = torch.empty((K,), dtype=torch.float32, device=x.device) if want_dbias else None
+    db = None
+    if want_dbias:
+        db = out_db.view(K) if out_db is not None else torch.empty((K,), dtype=torch.float32, device=x.device)
     algo = conv_algo() if algo is None else algo
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_WGRAD, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(x.device, nws) if nws else None
@@ -258,6 +263,13 @@ def join_wgrad(device: torch.device) -> None:
     if side is not None and _overlap["keep"].get(device.index):
         torch.cuda.current_stream(device).wait_stream(side)
         _overlap["keep"][device.index] = []
+
+
+def wgrad_side_stream_if_any(device: torch.device):
+    """The wgrad side stream if it holds kernels that have not been joined yet (else None): what a
+    consumer of weight gradients must wait for in addition to the current stream."""
+    side = _overlap["side"].get(device.index)
+    return side if (side is not None and _overlap["keep"].get(device.index)) else None
 
 
 def _wgrad_side_stream(device: torch.device):
@@ -321,16 +333,19 @@ def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var:
 
 
 def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = True,
-               dropout_p: float = 0.0, seed: int = 0, addend=None, want_dskip: bool = False):
-    """Returns (dx, dgamma, dbeta, dskip)."""
+               dropout_p: float = 0.0, seed: int = 0, addend=None, want_dskip: bool = False,
+               out_dgamma=None, out_dbeta=None):
+    """Returns (dx, dgamma, dbeta, dskip). out_dgamma / out_dbeta: optional fp32 [C] destinations."""
     _check_act(dy, "bn_act_bwd.dy")
     C = dy.shape[-1]
     rows = dy.numel() // C
     dx = torch.empty_like(dy)
     dskip = torch.empty_like(dy) if want_dskip else None
     affine = gamma is not None
-    dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
-    dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device) if affine else None
+    dgamma = dbeta = None
+    if affine:
+        dgamma = out_dgamma.view(C) if out_dgamma is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
+        dbeta = out_dbeta.view(C) if out_dbeta is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
     nws = _lib.load().b200_bn_workspace_bytes(rows, C) if affine else 0
     if affine:
         _drop_pending_stats(dy.device)
@@ -414,13 +429,13 @@ def linear_fwd(x, w, b):
     return y
 
 
-def linear_bwd(dy, x, w, want_dx=True):
+def linear_bwd(dy, x, w, want_dx=True, out_dw=None, out_db=None):
     _check_act(dy, "linear_bwd.dy")
     B, O = dy.shape
     I = x.shape[1]
     dx = torch.empty((B, I), dtype=torch.bfloat16, device=dy.device) if want_dx else None
-    dw = torch.empty((O, I), dtype=torch.float32, device=dy.device)
-    db = torch.empty((O,), dtype=torch.float32, device=dy.device)
+    dw = out_dw.view(O, I) if out_dw is not None else torch.empty((O, I), dtype=torch.float32, device=dy.device)
+    db = out_db.view(O) if out_db is not None else torch.empty((O,), dtype=torch.float32, device=dy.device)
     _lib.call("b200_linear_bwd", dy.data_ptr(), x.data_ptr(), w.data_ptr(), _p(dx), dw.data_ptr(),
               db.data_ptr(), B, I, O, _stream())
     return dx, dw, db

@@ -1,6 +1,6 @@
 """
-Whole-step CUDA-graph capture: forward + loss/metrics + backward + fused SGD update become ONE graph
-launch per step, removing ~200 host-side kernel launches (data parallel: see below).
+Whole-step CUDA-graph capture: forward + loss/metrics + backward + gradient exchange + fused SGD update
+become ONE graph launch per step, removing ~200 host-side kernel launches.
 
 The training step of the reference (resnet/algos/training.py:94-113) is host-driven op by op; on a
 B200 the WRN-28-10 step is a few milliseconds of GPU time, less than the Python time needed to
@@ -16,26 +16,209 @@ What keeps a replay equal to an eager step:
   * BN running statistics / num_batches_tracked are updated by kernels inside the graph;
   * cached bf16 filter copies are invalidated after every replay (eval after training sees the
     updated weights).
+Construction is free of side effects: parameters, BN buffers, optimizer state and the dropout step
+counter are snapshotted before the warm-up steps that precede a capture and restored after it, so
+the first call of the object is optimisation step number one (as in eager mode and in the reference).
 Inputs must keep the captured shape; other shapes (e.g. a ragged last batch) run eagerly.
 
-Data parallel (classifier is a DistributedDataParallel wrapper): the graph holds forward + backward of
-the LOCAL module (no DDP hooks run inside a capture); each replay is followed by ONE NCCL
-all-reduce (average) of the flat gradient buffer and the fused SGD launch. BatchNorm buffers stay
-per-rank during graphed training and are re-synchronised from rank 0 whenever the DDP wrapper runs a
-forward (evaluation, eager steps), which is where the reference's per-forward broadcast is observable.
+Data parallel (classifier is a DistributedDataParallel wrapper; reference: script.py:64-71, the stock
+DDP reducer): the gradient exchange of the reference — bucketed all-reduce (mean) overlapped with the
+rest of backward — is rebuilt for graph capture by FlatGradReducer below:
+  * ONE flat fp32 buffer holds every parameter gradient, laid out in REVERSE registration order (the
+    order in which backward produces them) and cut into ~25 MB buckets at parameter boundaries;
+  * every gradient kernel (wgrad, BN backward reduce, linear backward, conv bias) writes straight into
+    its slot, so there is no staging copy (a gradient that arrives elsewhere is copied in by the hook);
+  * a post-accumulate-grad hook per parameter counts a bucket down; when its last gradient has been
+    enqueued, the bucket's ncclAllReduce(avg) is issued on a communication stream that waits for the
+    compute stream and the wgrad side stream at that point. Inside a capture those waits become graph
+    edges, so each replay overlaps the collectives with the remaining backward kernels;
+  * the fused SGD launch waits for the communication stream and is part of the same graph.
+BatchNorm buffers stay per-rank during graphed training and are re-synchronised from rank 0 whenever
+the DDP wrapper runs a forward (evaluation, eager steps), which is where the reference's per-forward
+broadcast is observable.
 """
-from typing import Dict, Optional
+import os
+from typing import Dict, List, Optional
 
 import torch
 
 from pytorch_ddp_resnet_b200 import ops
 from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
-from pytorch_ddp_resnet_b200.architectures.layers import invalidate_weight_caches
+from pytorch_ddp_resnet_b200.architectures.layers import (BatchNorm2d, Conv2d, Linear,
+                                                         invalidate_weight_caches)
+
+DEFAULT_BUCKET_BYTES = 25 << 20
+
+
+def plan_buckets(sizes_reverse: List[int], bucket_bytes: int = DEFAULT_BUCKET_BYTES,
+                 last_bucket_bytes: Optional[int] = None):
+    """Cuts a list of gradient sizes (elements, already in reverse registration order) into contiguous
+    buckets of about `bucket_bytes`. Returns (offsets, bucket index per entry, [(lo, hi)] per bucket) in
+    elements; slots are 16-byte aligned. The bucket that completes last (the first layers of the
+    network) is exposed after backward, so it is kept small (`last_bucket_bytes`, default a quarter)."""
+    last_bucket_bytes = bucket_bytes // 4 if last_bucket_bytes is None else last_bucket_bytes
+    padded = [(n + 3) // 4 * 4 for n in sizes_reverse]
+    n = len(padded)
+    # tail bucket: the trailing entries (produced last by backward), at least one
+    tail_start, acc = n, 0
+    while tail_start > 0 and (acc + padded[tail_start - 1]) * 4 <= last_bucket_bytes:
+        acc += padded[tail_start - 1]
+        tail_start -= 1
+    if n and tail_start == n:
+        tail_start = n - 1
+    offsets, owner, ranges = [], [], []
+    lo = pos = 0
+    for i, sz in enumerate(padded):
+        if i == tail_start and pos > lo:
+            ranges.append((lo, pos))
+            lo = pos
+        offsets.append(pos)
+        owner.append(len(ranges))
+        pos += sz
+        if i < tail_start and (pos - lo) * 4 >= bucket_bytes:
+            ranges.append((lo, pos))
+            lo = pos
+    if pos > lo:
+        ranges.append((lo, pos))
+    return offsets, owner, ranges
+
+
+class FlatGradReducer:
+    """Flat gradient buffer + bucketed, backward-overlapped NCCL all-reduce (mean) for one module."""
+
+    def __init__(self, module: torch.nn.Module, device: torch.device, world: int,
+                 bucket_bytes: int = DEFAULT_BUCKET_BYTES, exchange: bool = True):
+        self.module, self.device, self.world = module, device, world
+        self.exchange = exchange and world > 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params[::-1]
+        offsets, owner, self.ranges = plan_buckets([p.numel() for p in self.params], bucket_bytes)
+        total = self.ranges[-1][1] if self.ranges else 0
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.slot = {id(p): self.flat[o:o + p.numel()] for p, o in zip(self.params, offsets)}
+        self.bucket_of = {id(p): b for p, b in zip(self.params, owner)}
+        self.bucket_size = [0] * len(self.ranges)
+        for b in owner:
+            self.bucket_size[b] += 1
+        self.pending = list(self.bucket_size)
+        self.launched = [False] * len(self.ranges)
+        self.active = False
+        self.copied = 0   # gradients that had to be copied into their slot (0 on the kernel path)
+        self.comm = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self._attach()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def _attach(self) -> None:
+        """Points every gradient-producing kernel of the module at its slot of the flat buffer."""
+        for m in self.module.modules():
+            if isinstance(m, Conv2d):
+                K, C, R, S = m.weight.shape
+                m.grad_out = self.slot[id(m.weight)].view(K, R, S, C)
+                if m.bias is not None:
+                    m.bias_grad_out = self.slot[id(m.bias)]
+            elif isinstance(m, BatchNorm2d):
+                m.grad_out = (self.slot[id(m.weight)], self.slot[id(m.bias)])
+            elif isinstance(m, Linear):
+                m.grad_out = (self.slot[id(m.weight)].view_as(m.weight), self.slot[id(m.bias)])
+
+    def detach(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        for m in self.module.modules():
+            if isinstance(m, Conv2d):
+                m.grad_out = m.bias_grad_out = None
+            elif isinstance(m, (BatchNorm2d, Linear)):
+                m.grad_out = None
+
+    # ---- one backward pass ---------------------------------------------------------------------
+    def begin(self) -> None:
+        self.pending = list(self.bucket_size)
+        self.launched = [False] * len(self.ranges)
+        self.active = True
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if not self.active:
+            return
+        slot = self.slot[id(p)]
+        if p.grad.data_ptr() != slot.data_ptr():
+            # a gradient that was not produced in place (a module without grad_out support, or autograd
+            # cloned it): move it into the flat buffer so that the exchange and the optimizer see one copy
+            dst = slot.as_strided(p.size(), p.stride())
+            dst.copy_(p.grad)
+            p.grad = dst
+            self.copied += 1
+        b = self.bucket_of[id(p)]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        self.launched[b] = True
+        if not self.exchange:
+            return
+        lo, hi = self.ranges[b]
+        if self.comm is None:   # host tensors (gloo): no streams, no AVG
+            torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.SUM)
+            self.flat[lo:hi].div_(self.world)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.comm.wait_stream(cur)
+        side = ops.wgrad_side_stream_if_any(self.device)
+        if side is not None:
+            self.comm.wait_stream(side)
+        with torch.cuda.stream(self.comm):
+            torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.AVG)
+
+    def finish(self) -> None:
+        """After backward: issues the buckets that never filled (parameters without a gradient) and makes
+        the current stream wait for every collective."""
+        self.active = False
+        for b in range(len(self.ranges)):
+            if not self.launched[b]:
+                self._launch(b)
+        if self.exchange and self.comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+
+class _Snapshot:
+    """Parameters, buffers, optimizer state and the dropout step counter of a training setup."""
+
+    def __init__(self, module, optimizer, device):
+        self.module, self.optimizer, self.device = module, optimizer, device
+        self.tensors = [(t, t.detach().clone()) for t in list(module.parameters()) + list(module.buffers())]
+        self.had_state = {id(p): (p in optimizer.state and len(optimizer.state[p]) > 0)
+                          for g in optimizer.param_groups for p in g["params"]}
+        self.opt_tensors = [(v, v.detach().clone()) for st in optimizer.state.values() for v in st.values()
+                            if torch.is_tensor(v)]
+        self.counter = ops.step_counter(device).clone()
+
+    def restore(self) -> bool:
+        """Returns True when optimizer state was created since the snapshot (it is zeroed, not deleted:
+        a captured graph has the 'seasoned' momentum update baked in, and with buf = 0 that update equals
+        torch's first step exactly when dampening = 0)."""
+        with torch.no_grad():
+            for t, c in self.tensors:
+                t.copy_(c)
+            for t, c in self.opt_tensors:
+                t.copy_(c)
+            created = False
+            for g in self.optimizer.param_groups:
+                for p in g["params"]:
+                    if not self.had_state.get(id(p), False) and p in self.optimizer.state:
+                        for v in self.optimizer.state[p].values():
+                            if torch.is_tensor(v):
+                                v.zero_()
+                                created = True
+            ops.step_counter(self.device).copy_(self.counter)
+        return created
 
 
 class GraphedTrainStep:
     def __init__(self, classifier, optimizer, x_example: torch.Tensor, y_example: torch.Tensor,
-                 warmup: Optional[int] = None):
+                 warmup: Optional[int] = None, bucket_bytes: int = DEFAULT_BUCKET_BYTES,
+                 exchange: bool = True):
+        """exchange=False captures the data-parallel step WITHOUT its collectives (same kernels): the
+        difference in step time is the exposed communication (SURVEY 8d timing protocol)."""
         if not x_example.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
         self.classifier, self.optimizer = classifier, optimizer
@@ -46,21 +229,22 @@ class GraphedTrainStep:
         self.local = classifier.module if self.is_ddp else classifier
         self.world = torch.distributed.get_world_size() if self.is_ddp else 1
         warmup = 3 if warmup is None else warmup
-        self.eager_steps = 0
-        self.flat = None
-        if self.is_ddp:
-            self._setup_flat_gradients()
+        self.reducer = FlatGradReducer(self.local, self.device, self.world, bucket_bytes, exchange) \
+            if self.is_ddp else None
         ops.step_counter(self.device)  # must exist before capture (an in-capture alloc would re-zero it)
         with torch.cuda.device(self.device):
             ops.bn_accumulators(self.device)  # likewise: zero-filled once, outside the graph
-        self.graph = torch.cuda.CUDAGraph()
+        was_training = classifier.training
         classifier.train()
+        snap = _Snapshot(self.local, optimizer, self.device)
+        # torch's first momentum step (buf = g) differs from the captured one (buf = m*buf + (1-d)*g on a
+        # zeroed buf) only when dampening != 0: such a first step runs eagerly
+        self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):   # >= 1: creates optimizer state and the NCCL communicator
                 self._eager(self.static_x, self.static_y)
-                self.eager_steps += 1
             if hasattr(optimizer, "sync_lr"):
                 optimizer.sync_lr()
         torch.cuda.current_stream(self.device).wait_stream(side)
@@ -69,84 +253,34 @@ class GraphedTrainStep:
         l0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             ops.tick(self.device)
-            self.static_metrics = self._forward_backward(self.local, self.static_x, self.static_y)
-            if not self.is_ddp:
-                self.optimizer.step()
-                self.optimizer.zero_grad(set_to_none=True)
+            self.static_metrics = self._forward_backward_exchange(self.static_x, self.static_y)
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
         self.launches_per_step = _lib.launch_count() - l0  # kernels of ours inside one replay
-        if self.is_ddp:
-            # .grad now aliases the graph's static gradient buffers; every replay rewrites them
-            self.grad_owners = [p for p in self.local.parameters() if p.grad is not None]
-            self.grads = [p.grad for p in self.grad_owners]
-            self.launches_per_step += 1  # the SGD launch that follows each replay
-            self._reduce_and_step()      # finish the step that the capture pass computed
+        torch.cuda.synchronize(self.device)
+        created = snap.restore()
+        self.eager_first = created and any(g.get("dampening", 0) != 0 and g.get("momentum", 0) != 0
+                                           for g in optimizer.param_groups)
+        if self.eager_first:
+            optimizer.state.clear()
         invalidate_weight_caches()
+        if not was_training:
+            classifier.eval()
 
-    def _setup_flat_gradients(self) -> None:
-        """One flat fp32 buffer holds every parameter gradient, so the exchange step is a single NCCL
-        all-reduce. Conv filter gradients (99.9 % of the bytes) are written into it directly by the wgrad
-        kernels (Conv2d.grad_out); the small BN / bias / linear gradients are copied in after backward."""
-        from pytorch_ddp_resnet_b200.architectures.layers import Conv2d
-        params = [p for p in self.local.parameters() if p.requires_grad]
-        offsets, total = {}, 0
-        for p in params:
-            offsets[id(p)] = total
-            total += (p.numel() + 3) // 4 * 4  # 16-byte aligned slots
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.flat_views = {}
-        for p in params:
-            o = offsets[id(p)]
-            self.flat_views[id(p)] = self.flat[o:o + p.numel()]
-        self.direct = set()
-        for m in self.local.modules():
-            if isinstance(m, Conv2d):
-                K, C, R, S = m.weight.shape
-                m.grad_out = self.flat_views[id(m.weight)].view(K, R, S, C)
-                self.direct.add(id(m.weight))
-        self.flat_params = params
-
-    def _gather_small_grads(self):
-        """(flat views, gradient tensors) of the parameters whose kernels do not write into `flat`."""
-        dst, src = [], []
-        for p in self.flat_params:
-            if id(p) in self.direct or p.grad is None:
-                continue
-            dst.append(self.flat_views[id(p)].view_as(p.grad))
-            src.append(p.grad)
-        return dst, src
-
-    @staticmethod
-    def _forward_backward(module, x, y) -> Dict[str, torch.Tensor]:
-        import os
-        m = compute_losses_and_metrics(logits=module(x), labels=y)
+    def _forward_backward_exchange(self, x, y) -> Dict[str, torch.Tensor]:
+        m = compute_losses_and_metrics(logits=self.local(x), labels=y)
+        if self.reducer is not None:
+            self.reducer.begin()
         # wgrad kernels run on a side stream, concurrently with the dgrad / BN-backward chain
         with ops.wgrad_overlap(x.device, enabled=os.environ.get("B200_WGRAD_OVERLAP", "1") != "0"):
             m["loss"].backward()
+        if self.reducer is not None:
+            self.reducer.finish()
         return {k: v.detach() for k, v in m.items()}
-
-    def _exchange(self) -> None:
-        """Gradient averaging over ranks: stage the small gradients, then ONE NCCL all-reduce of the flat
-        buffer, then point every .grad at its (now averaged) slot."""
-        dst, src = self._gather_small_grads()
-        if dst:
-            torch._foreach_copy_(dst, src)
-        torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
-        for p in self.flat_params:
-            if p.grad is not None and id(p) not in self.direct:
-                p.grad = self.flat_views[id(p)].view_as(p.grad)
-
-    def _reduce_and_step(self) -> None:
-        # restore the aliases of the graph's static gradient tensors for the staging copy
-        for p, g in zip(self.grad_owners, self.grads):
-            p.grad = g
-        self._exchange()
-        self.optimizer.step()
 
     def _eager(self, x, y) -> Dict[str, torch.Tensor]:
         """One un-captured optimisation step with the same maths as a replay."""
-        m = self._forward_backward(self.local, x, y)
-        if self.is_ddp:
-            self._exchange()
+        m = self._forward_backward_exchange(x, y)
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
         return m
@@ -157,21 +291,16 @@ class GraphedTrainStep:
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One optimisation step. x / y may live on the host (pinned => asynchronous copy)."""
-        if not self.matches(x, y):
+        if not self.matches(x, y) or self.eager_first:
             self.classifier.train()
-            if self.is_ddp:  # detach the static gradient buffers for the duration of the eager step
-                self.optimizer.zero_grad(set_to_none=True)
+            self.eager_first = False
             out = self._eager(x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True))
-            if self.is_ddp:
-                for p, g in zip(self.grad_owners, self.grads):
-                    p.grad = g
+            invalidate_weight_caches()
             return out
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()
-        if self.is_ddp:
-            self._reduce_and_step()
         invalidate_weight_caches()
         return self.static_metrics

@@ -14,6 +14,13 @@ import torch
 from pytorch_ddp_resnet_b200 import ops
 
 
+def _same_layout(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Same element order in memory (strides of size-1 dimensions do not matter)."""
+    if a.shape != b.shape:
+        return False
+    return all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n > 1)
+
+
 class FusedSGD(torch.optim.SGD):
     _step_supports_amp_scaling = True  # GradScaler hands us grad_scale / found_inf, no host sync
 
@@ -94,9 +101,14 @@ class FusedSGD(torch.optim.SGD):
                 g = p.grad
                 if g.is_sparse:
                     raise RuntimeError("FusedSGD does not support sparse gradients")
-                if g.dtype != torch.float32 or g.stride() != p.stride():
+                if g.dtype != torch.float32 or not _same_layout(g, p):
                     g = torch.empty_like(p).copy_(g)
                 state = self.state[p]
+                buf0 = state.get("momentum_buffer")
+                if buf0 is not None and not _same_layout(buf0, p):
+                    # e.g. a reference checkpoint: NCHW-contiguous buffers for channels_last parameters;
+                    # the kernel walks param / grad / buffer as flat memory, so they must share strides
+                    state["momentum_buffer"] = torch.empty_like(p).copy_(buf0)
                 if group["momentum"] != 0 and state.get("momentum_buffer") is None:
                     state["momentum_buffer"] = torch.empty_like(p)  # written by the kernel (buf = g)
                     fresh.append((p, g, state["momentum_buffer"]))

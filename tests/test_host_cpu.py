@@ -109,6 +109,21 @@ def test_config_and_checkpoint_roundtrip(tmp_path):
     assert [perf.observe(unit="epoch", loss=l) for l in (1.0, 2.0, 0.5)] == [True, False, True]
 
 
+def test_plan_buckets_layout():
+    from pytorch_ddp_resnet_b200.utils.graph_util import plan_buckets
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    m = ResNet("c3,160,3,1,1 r4 r4 r4 n a ap8,1,0 fc640,10", True, True, 0.3)
+    sizes = [p.numel() for p in m.parameters()][::-1]
+    offsets, owner, ranges = plan_buckets(sizes)
+    assert len(offsets) == len(owner) == len(sizes) == 80
+    assert ranges[0][0] == 0 and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert ranges[-1][1] >= sum(sizes) and all(o % 4 == 0 for o in offsets)   # 16-byte aligned slots
+    assert owner == sorted(owner) and owner[-1] == len(ranges) - 1
+    mb = [(hi - lo) * 4 / 2 ** 20 for lo, hi in ranges]
+    assert all(20 < v < 40 for v in mb[:-1]) and mb[-1] <= 25 / 4 + 1e-6   # small exposed tail bucket
+    assert plan_buckets([]) == ([], [], []) and plan_buckets([10])[2] == [(0, 12)]
+
+
 # ---- N > 1 host logic on CPU: gloo, world_size 2 -------------------------------------------------
 def _worker(rank, world, port, tmp):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -150,6 +165,33 @@ def _worker(rank, world, port, tmp):
     gathered = [torch.zeros_like(w) for _ in range(world)]
     dist.all_gather(gathered, w)
     assert torch.equal(gathered[0], gathered[1])
+    # (3) FlatGradReducer (the graph-mode gradient exchange): reverse-order flat buffer, bucketed
+    #     all-reduce issued from post-accumulate-grad hooks, .grad ends up as the averaged slot
+    from pytorch_ddp_resnet_b200.utils.graph_util import FlatGradReducer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 50), torch.nn.ReLU(), torch.nn.Linear(50, 30), torch.nn.ReLU(),
+                              torch.nn.Linear(30, 4))
+    red = FlatGradReducer(net, torch.device("cpu"), world, bucket_bytes=4096)
+    assert len(red.ranges) >= 3 and red.ranges[0][0] == 0
+    assert red.bucket_of[id(net[4].bias)] == 0 and red.bucket_of[id(net[0].weight)] == len(red.ranges) - 1
+    xg = torch.Generator().manual_seed(10 + rank)
+    xin = torch.randn(5, 6, generator=xg)
+    for _ in range(2):   # twice: begin() must re-arm the buckets
+        for prm in net.parameters():
+            prm.grad = None
+        red.begin()
+        net(xin).square().sum().backward()
+        red.finish()
+        assert all(red.launched) and red.copied > 0
+        mine = [prm.grad.clone() for prm in net.parameters()]
+        for prm in net.parameters():
+            prm.grad = None
+        net(xin).square().sum().backward()   # hooks inactive: plain local gradients
+        for prm, avg in zip(net.parameters(), mine):
+            loc = prm.grad.clone()
+            dist.all_reduce(loc)
+            assert torch.allclose(avg, loc / world, atol=1e-6), "reducer != mean of local gradients"
+    red.detach()
     dist.barrier()
     if rank == 0:
         names = sorted(os.listdir(tmp))
