@@ -243,16 +243,19 @@ def test_cuda_graph_step_equals_eager_steps():
     o2 = get_optimizer("SGD", m2, dict(SGD))
     sched = torch.optim.lr_scheduler.MultiStepLR(o2, milestones=[5], gamma=0.1)
     sched1 = torch.optim.lr_scheduler.MultiStepLR(o1, milestones=[5], gamma=0.1)
-    warm = 3
-    step = GraphedTrainStep(m2, o2, xs[0], ys[0], warmup=warm)  # 3 eager steps on xs[0] inside
-    for _ in range(warm):
-        sched.step()
+    before = {k: v.clone() for k, v in m2.state_dict().items()}
+    step = GraphedTrainStep(m2, o2, xs[0], ys[0], warmup=3)   # warm-up + capture leave no trace
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, before[k]), f"GraphedTrainStep construction changed {k}"
+    assert len(o2.state) == 0 or all(float(b.abs().max()) == 0 for st in o2.state.values() for b in st.values()
+                                     if torch.is_tensor(b))
+    warm = 0
     losses2 = []
     for i in range(6):
         losses2.append(step(xs[i], ys[i])["loss"].item())
         sched.step()
     losses1 = []
-    for i in [0] * warm + list(range(6)):
+    for i in range(6):
         l = compute_losses_and_metrics(logits=m1(xs[i]), labels=ys[i])["loss"]
         l.backward(); o1.step(); o1.zero_grad(set_to_none=True); sched1.step()
         losses1.append(l.item())
