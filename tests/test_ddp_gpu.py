@@ -64,9 +64,31 @@ def _worker(rank, world, port, use_graph):
     opt = get_optimizer("SGD", ddp, dict(SGD))
     opt.zero_grad(set_to_none=True)
     if use_graph:
-        step = GraphedTrainStep(ddp, opt, x, y)
+        # reference run: the same three steps with stock DDP, eagerly, on a copy of the replica
+        twin = ResNet(SPEC, True, True, 0.0).cuda().train()
+        twin.load_state_dict(init)
+        twin_ddp = wrap_ddp(twin, torch.device("cuda", rank))
+        twin_opt = get_optimizer("SGD", twin_ddp, dict(SGD))
+        for _ in range(3):
+            compute_losses_and_metrics(logits=twin_ddp(x), labels=y)["loss"].backward()
+            twin_opt.step()
+            twin_opt.zero_grad(set_to_none=True)
+        step = GraphedTrainStep(ddp, opt, x, y, bucket_bytes=64 << 10)   # small buckets: several collectives
+        assert len(step.reducer.ranges) >= 3
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, init[k]), f"GraphedTrainStep construction changed {k}"
         for _ in range(3):
             step(x, y)
+        assert step.reducer.copied == 0, "a gradient kernel did not write into the flat buffer"
+        # graphed DDP == eager DDP (bucketed exchange inside the graph, no spurious steps)
+        # (BN buffers: stock DDP broadcasts rank 0's before every forward, graphed training keeps them
+        #  per rank until the wrapper's next forward, so they are compared on rank 0 only)
+        mine = dict(model.named_parameters()) if rank else model.state_dict()
+        theirs = dict(twin.named_parameters()) if rank else twin.state_dict()
+        for n, p in mine.items():
+            q = theirs[n]
+            err = ((p.float() - q.float()).norm() / q.float().norm().clamp_min(1e-6)).item()
+            assert err < 2e-3, ("graph DDP != eager DDP", n, err)
     else:
         for _ in range(3):
             compute_losses_and_metrics(logits=ddp(x), labels=y)["loss"].backward()
