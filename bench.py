@@ -490,11 +490,21 @@ def run_ours(args):
     h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 8
     d2h = 4
 
-    if world > 1:
+    def leave():
+        """Multi-rank exit: release the graphs that hold NCCL kernels, meet at a barrier, and leave without
+        the process-group destructor (it was seen to hang once captured collectives exist)."""
+        if world == 1:
+            return
+        if not args.eager:
+            graphed.close()
         dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
 
     # ---- roofline + tensor-pipe utilisation (rank 0) ------------------------------------------------
@@ -578,8 +588,7 @@ def run_ours(args):
                        "patched to bfloat16, fp16 = its literal default (autocast + GradScaler)")
         line["gpu_reference"] = ref
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():

@@ -285,6 +285,16 @@ class GraphedTrainStep:
         self.optimizer.zero_grad(set_to_none=True)
         return m
 
+    def close(self) -> None:
+        """Releases the captured graph (and the NCCL kernels it holds) and detaches the reducer. Call it
+        before torch.distributed.destroy_process_group(); the object cannot step afterwards."""
+        torch.cuda.synchronize(self.device)
+        self.graph.reset()
+        self.graph = None
+        if self.reducer is not None:
+            self.reducer.detach()
+            self.reducer = None
+
     def matches(self, x: torch.Tensor, y: torch.Tensor) -> bool:
         return (x.shape == self.static_x.shape and x.dtype == self.static_x.dtype
                 and y.shape == self.static_y.shape and self.classifier.training)

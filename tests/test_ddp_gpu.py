@@ -65,8 +65,9 @@ def _worker(rank, world, port, use_graph):
     opt.zero_grad(set_to_none=True)
     if use_graph:
         # reference run: the same three steps with stock DDP, eagerly, on a copy of the replica
+        before = {k: v.clone() for k, v in model.state_dict().items()}   # part (1) updated the BN buffers
         twin = ResNet(SPEC, True, True, 0.0).cuda().train()
-        twin.load_state_dict(init)
+        twin.load_state_dict(before)
         twin_ddp = wrap_ddp(twin, torch.device("cuda", rank))
         twin_opt = get_optimizer("SGD", twin_ddp, dict(SGD))
         for _ in range(3):
@@ -76,7 +77,7 @@ def _worker(rank, world, port, use_graph):
         step = GraphedTrainStep(ddp, opt, x, y, bucket_bytes=64 << 10)   # small buckets: several collectives
         assert len(step.reducer.ranges) >= 3
         for k, v in model.state_dict().items():
-            assert torch.equal(v, init[k]), f"GraphedTrainStep construction changed {k}"
+            assert torch.equal(v, before[k]), f"GraphedTrainStep construction changed {k}"
         for _ in range(3):
             step(x, y)
         assert step.reducer.copied == 0, "a gradient kernel did not write into the flat buffer"
@@ -89,6 +90,7 @@ def _worker(rank, world, port, use_graph):
             q = theirs[n]
             err = ((p.float() - q.float()).norm() / q.float().norm().clamp_min(1e-6)).item()
             assert err < 2e-3, ("graph DDP != eager DDP", n, err)
+        step.close()   # graphs that hold NCCL kernels are released before the process group goes away
     else:
         for _ in range(3):
             compute_losses_and_metrics(logits=ddp(x), labels=y)["loss"].backward()
@@ -100,7 +102,10 @@ def _worker(rank, world, port, use_graph):
         dist.broadcast(ref, 0)
         assert torch.equal(ref, p.detach()), f"replicas diverged at {n}"
     dist.barrier()
+    import signal
+    signal.alarm(60)   # a hanging teardown must fail the test, not stall the box
     dist.destroy_process_group()
+    signal.alarm(0)
 
 
 @pytest.mark.parametrize("use_graph", [False, True])

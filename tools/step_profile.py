@@ -7,7 +7,7 @@ from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics
 from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
 from pytorch_ddp_resnet_b200.utils.optim_util import get_optimizer
 import bench
-spec = sys.argv[1] if len(sys.argv) > 1 else bench.SPEC
+spec = sys.argv[1] if len(sys.argv) > 1 else bench.resolve_config("wrn28", 1)["spec"]
 torch.manual_seed(0)
 m = ResNet(spec, True, True, 0.3).cuda().train()
 opt = get_optimizer("SGD", m, dict(bench.SGD))
