@@ -76,16 +76,20 @@ int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias, cons
                       void* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
                       int algo, void* ws, size_t ws_bytes, b200_stream_t stream);
 
-/* b200_conv2d_fprop that ALSO adds, per output channel k, sum(y[..,k]) and sum(y[..,k]^2) over all
- * N*P*Q output pixels (of the bf16 values it stores) into the BN accumulator workspace `stats_ws`
- * (b200_bn_workspace_bytes(rows, K) bytes, contract below: zero on entry). The batch norm that follows a
- * conv in the reference (residual_block.py:69-98) then needs no pass of its own over y: call
- * b200_bn_stats_finalize on the same workspace. The tcgen05 SM-pair kernels do this in their epilogue;
- * other conv paths run one accumulate-only reduction over y, so the result is the same either way. */
+/* b200_conv2d_fprop that ALSO computes the batch statistics of its output for the batch norm that follows a
+ * conv in the reference (residual_block.py:69-98), so that BN needs no pass of its own over y. Per output
+ * channel k, sum(y[..,k]) and sum(y[..,k]^2) over all N*P*Q output pixels (of the bf16 values it stores) are
+ * accumulated in the BN accumulator workspace `stats_ws` (b200_bn_workspace_bytes(rows, K) bytes, contract
+ * below: zero on entry). With mean / invstd non-NULL (fp32 [K]) the CTA that finishes last turns the sums
+ * into mean and invstd = rsqrt(biased var + eps) and clears the workspace: no further launch is needed (the
+ * running statistics are then updated by b200_bn_act_fwd or b200_bn_running_update). With mean == invstd ==
+ * NULL the sums stay in the workspace for b200_bn_stats_finalize. The tcgen05 SM-pair kernels do all of this
+ * in their epilogue; other conv paths run one reduction pass over y, so the result is the same either way. */
 int b200_conv2d_fprop_stats(const void* x, const void* w_krsc, const float* bias, const void* residual,
                             void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
                             int pad, int algo, void* ws, size_t ws_bytes, void* stats_ws,
-                            size_t stats_ws_bytes, b200_stream_t stream);
+                            size_t stats_ws_bytes, float eps, float* mean, float* invstd,
+                            b200_stream_t stream);
 
 /* dx = bf16( conv_transpose(dy, w) ) ; if addend: dx = bf16(dx + addend) (skip-path gradient).
  * w_crsk is the transposed bf16 filter from b200_weight_prep. */
@@ -124,25 +128,41 @@ int b200_bn_stats_finalize(int64_t rows, int C, float eps, float momentum, float
                            float* running_mean, float* running_var, int64_t* num_batches_tracked,
                            void* ws, size_t ws_bytes, b200_stream_t stream);
 
+/* running_mean / running_var (momentum, unbiased variance) and num_batches_tracked from a batch mean /
+ * invstd pair that b200_conv2d_fprop_stats produced (aten::native_batch_norm's buffer update). */
+int b200_bn_running_update(const float* mean, const float* invstd, int64_t rows, int C, float eps,
+                           float momentum, float* running_mean, float* running_var,
+                           int64_t* num_batches_tracked, b200_stream_t stream);
+
 /* y = dropout( act( (x - mean) * invstd * gamma + beta [+ skip] ) ).
  * stat_is_var != 0: `invstd` holds a variance (eval mode, running stats) and rsqrt(var+eps) is applied.
  * gamma/beta/mean/invstd NULL  => the affine/normalise step is skipped (plain act/dropout/add).
  * relu: 0/1. dropout_p in [0,1): keep mask from the counter RNG keyed by (seed, element index);
  * seed_offset (device uint64 scalar, may be NULL) is a step counter folded into the seed on the
  * device, so a captured CUDA graph draws a fresh mask at every replay (see b200_tick).
- * x is [N,H,W,C]; skip addressing per skip_mode (skip_C = channel count of the skip tensor). */
+ * x is [N,H,W,C]; skip addressing per skip_mode (skip_C = channel count of the skip tensor).
+ * running_mean (may be NULL): also perform the running-statistics update of b200_bn_running_update with
+ * these mean / invstd, eps, `momentum` and rows = N*H*W (training forward whose statistics came out of
+ * b200_conv2d_fprop_stats: saves the separate launch).
+ * mask_out (may be NULL): N*H*W*C/8 bytes, one per (pixel, 8-channel group); bit j set = channel 8g+j passed
+ * the ReLU gate (if relu) and was kept by the dropout (if dropout_p > 0). b200_bn_act_bwd takes it instead of
+ * y: 0.125 instead of 2 bytes per element of backward traffic in each of its two kernels. */
 int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int C, const float* mean,
                     const float* invstd, int stat_is_var, float eps, const float* gamma,
                     const float* beta, const void* skip, int skip_mode, int skip_C, int relu,
-                    float dropout_p, uint64_t seed, const uint64_t* seed_offset, b200_stream_t stream);
+                    float dropout_p, uint64_t seed, const uint64_t* seed_offset, float* running_mean,
+                    float* running_var, int64_t* num_batches_tracked, float momentum, void* mask_out,
+                    b200_stream_t stream);
 
-/* Backward of b200_bn_act_fwd. y is the forward OUTPUT (its non-zero pattern is the relu mask; may
- * be NULL when relu == 0), x the forward input, dy the gradient w.r.t. y. The dropout mask is
- * regenerated from (seed, element index). With g = dy * dropmask * 1/(1-p) * relumask this produces
- * dbeta = sum(g), dgamma = sum(g * xhat), dx (bf16) and, if dskip != NULL, g itself (the gradient
- * flowing to the skip operand, output-shaped). If addend != NULL: dx = bf16(dx + addend) (same
- * shape; the strided skip gradients use b200_upsample_add). gamma NULL => no normalisation (dx = g). */
-int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
+/* Backward of b200_bn_act_fwd. x is the forward input, dy the gradient w.r.t. the forward output y.
+ * The combined ReLU + dropout mask comes from `mask` (the bytes b200_bn_act_fwd wrote to mask_out) when it is
+ * non-NULL; else from the non-zero pattern of y when relu != 0 (y may then not be NULL); without ReLU and
+ * without mask the dropout mask is regenerated from (seed, element index).
+ * With g = dy * dropmask * 1/(1-p) * relumask this produces dbeta = sum(g), dgamma = sum(g * xhat), dx (bf16)
+ * and, if dskip != NULL, g itself (the gradient flowing to the skip operand, output-shaped). If addend !=
+ * NULL: dx = bf16(dx + addend) (same shape; the strided skip gradients use b200_upsample_add).
+ * gamma NULL => no normalisation (dx = g). */
+int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, const void* x, void* dx, void* dskip,
                     const void* addend, int64_t rows, int C, const float* mean, const float* invstd,
                     const float* gamma, float* dgamma, float* dbeta, int relu, float dropout_p,
                     uint64_t seed, const uint64_t* seed_offset, void* ws, size_t ws_bytes,

@@ -30,7 +30,9 @@ SIGNATURES = {
     "b200_weight_prep_multi": (c_int, [_P, c_int, _P]),
     "b200_conv2d_workspace_bytes": (c_size_t, [c_int] + _CONV_DIMS + [c_int]),
     "b200_conv2d_fprop": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
-    "b200_conv2d_fprop_stats": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P, c_size_t, _P]),
+    "b200_conv2d_fprop_stats": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P, c_size_t,
+                                        c_float, _P, _P, _P]),
+    "b200_bn_running_update": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
     "b200_bn_stats_finalize": (c_int, [c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_conv2d_dgrad": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
     "b200_conv2d_wgrad": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
@@ -39,8 +41,8 @@ SIGNATURES = {
     "b200_bn_stats": (c_int, [_P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P,
                               c_size_t, _P]),
     "b200_bn_act_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_float, _P, _P,
-                                _P, c_int, c_int, c_int, c_float, c_uint64, _P, _P]),
-    "b200_bn_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int,
+                                _P, c_int, c_int, c_int, c_float, c_uint64, _P, _P, _P, _P, c_float, _P, _P]),
+    "b200_bn_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int,
                                 c_float, c_uint64, _P, _P, c_size_t, _P]),
     "b200_subsample2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -194,9 +194,14 @@ class BatchNorm2d(tc.nn.Module):
         return dict(out_dgamma=self.grad_out[0], out_dbeta=self.grad_out[1]) if self.grad_out else {}
 
     def batch_stats(self, x_nhwc):
-        """Training statistics of x (+ in-place running-stat update)."""
-        return ops.bn_stats(x_nhwc, self.eps, self.momentum, self.running_mean, self.running_var,
-                            self.num_batches_tracked)
+        """Training statistics of x -> (mean, invstd, fwd_kwargs). The running statistics are updated either
+        by the statistics launch itself or, when the conv that produced x already computed mean / invstd,
+        by the bn_act_fwd launch that must follow with **fwd_kwargs."""
+        mean, invstd, deferred = ops.bn_batch_stats(x_nhwc, self.eps, self.momentum, self.running_mean,
+                                                    self.running_var, self.num_batches_tracked)
+        kw = dict(running=(self.running_mean, self.running_var, self.num_batches_tracked, self.momentum)) \
+            if deferred else {}
+        return mean, invstd, kw
 
     def forward(self, x):
         return BnActFn.apply(x, self.weight, self.bias, self, False)
@@ -303,9 +308,12 @@ class BnActFn(torch.autograd.Function):
             y = ops.bn_act_fwd(xh, relu=relu)
             ctx.save_for_backward(y)
         elif bn.training:
-            mean, invstd = bn.batch_stats(xh)
-            y = ops.bn_act_fwd(xh, mean, invstd, gamma, beta, relu=relu)
-            ctx.save_for_backward(xh, y, mean, invstd, gamma)
+            mean, invstd, kw = bn.batch_stats(xh)
+            if relu:
+                y, mask = ops.bn_act_fwd(xh, mean, invstd, gamma, beta, relu=True, want_mask=True, **kw)
+            else:
+                y, mask = ops.bn_act_fwd(xh, mean, invstd, gamma, beta, relu=False, **kw), None
+            ctx.save_for_backward(xh, mask, mean, invstd, gamma)
             ctx.bn = bn
         else:
             y = ops.bn_act_fwd(xh, bn.running_mean, bn.running_var, gamma, beta, stat_is_var=True,
@@ -321,8 +329,8 @@ class BnActFn(torch.autograd.Function):
             return as_nchw_view(dx), None, None, None, None
         if not ctx.train:
             raise B200Error("backward through eval-mode BatchNorm is not supported")
-        xh, y, mean, invstd, gamma = ctx.saved_tensors
-        dx, dgamma, dbeta, _ = ops.bn_act_bwd(g, y, xh, mean, invstd, gamma, relu=ctx.relu,
+        xh, mask, mean, invstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta, _ = ops.bn_act_bwd(g, None, xh, mean, invstd, gamma, relu=ctx.relu, mask=mask,
                                               **ctx.bn.grad_dst())
         return as_nchw_view(dx), dgamma, dbeta, None, None
 

@@ -57,17 +57,21 @@ class _BlockFn(torch.autograd.Function):
         def bn_args(j, t):
             m = norms[j]
             if training:
-                mean, invstd = m.batch_stats(t)
-                return dict(mean=mean, invstd=invstd, gamma=gammas[j], beta=betas[j])
+                mean, invstd, kw = m.batch_stats(t)
+                return dict(mean=mean, invstd=invstd, gamma=gammas[j], beta=betas[j], **kw)
             return dict(mean=m.running_mean, invstd=m.running_var, gamma=gammas[j], beta=betas[j],
                         stat_is_var=True, eps=m.eps)
 
-        saved_in, saved_act, saved_conv, stats = [], [], [], []
+        saved_in, saved_act, saved_conv, stats, masks = [], [], [], [], []
         h = xh
         if preact:
             for j, c in enumerate(convs):
                 st = bn_args(j, h)
-                a = ops.bn_act_fwd(h, relu=True, dropout_p=p, seed=seeds[j], **st)
+                if training:   # the ReLU / dropout bit mask replaces y in the backward kernels
+                    a, mk = ops.bn_act_fwd(h, relu=True, dropout_p=p, seed=seeds[j], want_mask=True, **st)
+                else:
+                    a, mk = ops.bn_act_fwd(h, relu=True, dropout_p=p, seed=seeds[j], **st), None
+                masks.append(mk)
                 saved_in.append(h)          # BN input
                 saved_act.append(a)         # conv input
                 stats.append(st)
@@ -90,11 +94,15 @@ class _BlockFn(torch.autograd.Function):
                 saved_act.append(d)         # conv input
                 saved_conv.append(cj)       # BN input
                 stats.append(st)
+                kw = dict(want_mask=True) if training else {}
                 if j < n - 1:
-                    h = ops.bn_act_fwd(cj, relu=True, **st)
+                    h = ops.bn_act_fwd(cj, relu=True, **st, **kw)
                 else:
-                    h = ops.bn_act_fwd(cj, relu=True, skip=skip, skip_mode=skip_mode, **st)
-                saved_in.append(h)          # BN output (relu mask source)
+                    h = ops.bn_act_fwd(cj, relu=True, skip=skip, skip_mode=skip_mode, **st, **kw)
+                if training:
+                    h, mk = h
+                    masks.append(mk)
+                saved_in.append(h)          # BN output
             out = h
 
         ctx.block, ctx.training, ctx.p, ctx.seeds = block, training, p, seeds
@@ -103,6 +111,7 @@ class _BlockFn(torch.autograd.Function):
         ctx.xsub = xsub
         ctx.xh = xh
         ctx.saved_in, ctx.saved_act, ctx.saved_conv = saved_in, saved_act, saved_conv
+        ctx.masks = masks
         ctx.stats = stats
         ctx.skip_mode = skip_mode
         ctx.need_dx = x.requires_grad
@@ -136,15 +145,15 @@ class _BlockFn(torch.autograd.Function):
                 da = ops.conv_dgrad(cur, ctx.wt[j], (a.shape[1], a.shape[2]), c.stride, c.padding)
                 addend = dskip if (j == 0 and identity) else None
                 cur, dgs[j], dbs[j], _ = ops.bn_act_bwd(
-                    da, a, hin, st["mean"], st["invstd"], st["gamma"], relu=True, dropout_p=p,
-                    seed=seeds[j], addend=addend, **norms[j].grad_dst())
+                    da, None, hin, st["mean"], st["invstd"], st["gamma"], relu=True, dropout_p=p,
+                    seed=seeds[j], addend=addend, mask=ctx.masks[j], **norms[j].grad_dst())
             dx = cur
         else:
             # last BN: relu(bn(c_n) + skip)
             st = ctx.stats[n - 1]
             cur, dgs[n - 1], dbs[n - 1], dskip = ops.bn_act_bwd(
-                g, ctx.saved_in[n - 1], ctx.saved_conv[n - 1], st["mean"], st["invstd"], st["gamma"],
-                relu=True, want_dskip=True, **norms[n - 1].grad_dst())
+                g, None, ctx.saved_conv[n - 1], st["mean"], st["invstd"], st["gamma"],
+                relu=True, want_dskip=True, mask=ctx.masks[n - 1], **norms[n - 1].grad_dst())
             for j in range(n - 1, -1, -1):
                 c = convs[j]
                 d = ctx.saved_act[j]
@@ -160,8 +169,8 @@ class _BlockFn(torch.autograd.Function):
                 if j > 0:
                     st = ctx.stats[j - 1]
                     cur, dgs[j - 1], dbs[j - 1], _ = ops.bn_act_bwd(
-                        dd, ctx.saved_in[j - 1], ctx.saved_conv[j - 1], st["mean"], st["invstd"],
-                        st["gamma"], relu=True, **norms[j - 1].grad_dst())
+                        dd, None, ctx.saved_conv[j - 1], st["mean"], st["invstd"],
+                        st["gamma"], relu=True, mask=ctx.masks[j - 1], **norms[j - 1].grad_dst())
                 else:
                     cur = dd
             dx = cur

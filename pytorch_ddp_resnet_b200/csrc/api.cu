@@ -415,7 +415,7 @@ template <int KC, int MT, bool STATS>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                             int wcols, const TapTable& taps, void* out, const void* residual,
                             const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
-                            cudaStream_t st) {
+                            const EpiStatsFinal& fin, cudaStream_t st) {
   const int max_dyn = 228352;
   B200_CUDA(ensure_max_smem<conv_tc2h_kernel<KC, MT, STATS>>(max_dyn));
   ConvHaloArgs a;
@@ -445,6 +445,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
   a.stats = stats;
+  a.fin = fin;
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, pw, HALO_PH, 1)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
@@ -494,7 +495,11 @@ static int launch_conv_tc_cs(int cs, const CUtensorMap& tmA, const CUtensorMap& 
 static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                        int wcols, const TapTable& taps, void* out, const void* residual,
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
-                       double* stats = nullptr, bool* stats_fused = nullptr) {
+                       double* stats = nullptr, bool* stats_fused = nullptr,
+                       const EpiStatsFinal* finp = nullptr) {
+  EpiStatsFinal fin;
+  memset(&fin, 0, sizeof(fin));
+  if (finp) fin = *finp;
   // stats != nullptr: the SM-pair kernels also accumulate the per-channel sum / sum of squares of the
   // output (fused BN statistics); *stats_fused says whether the kernel that ran did it
   if (stats_fused) *stats_fused = false;
@@ -527,14 +532,14 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
 #define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw
       if (stats && !mt2 && BN <= EPI_STATS_MAX_BN) {
         *stats_fused = true;
-        if (KC == 64) return launch_conv_tc2h<64, 1, true>(B200_HALO_ARGS, stats, st);
-        return launch_conv_tc2h<32, 1, true>(B200_HALO_ARGS, stats, st);
+        if (KC == 64) return launch_conv_tc2h<64, 1, true>(B200_HALO_ARGS, stats, fin, st);
+        return launch_conv_tc2h<32, 1, true>(B200_HALO_ARGS, stats, fin, st);
       }
       if (KC == 64)
-        return mt2 ? launch_conv_tc2h<64, 2, false>(B200_HALO_ARGS, nullptr, st)
-                   : launch_conv_tc2h<64, 1, false>(B200_HALO_ARGS, nullptr, st);
-      return mt2 ? launch_conv_tc2h<32, 2, false>(B200_HALO_ARGS, nullptr, st)
-                 : launch_conv_tc2h<32, 1, false>(B200_HALO_ARGS, nullptr, st);
+        return mt2 ? launch_conv_tc2h<64, 2, false>(B200_HALO_ARGS, nullptr, fin, st)
+                   : launch_conv_tc2h<64, 1, false>(B200_HALO_ARGS, nullptr, fin, st);
+      return mt2 ? launch_conv_tc2h<32, 2, false>(B200_HALO_ARGS, nullptr, fin, st)
+                 : launch_conv_tc2h<32, 1, false>(B200_HALO_ARGS, nullptr, fin, st);
 #undef B200_HALO_ARGS
     }
   }
@@ -555,6 +560,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
     if (stats && BN <= EPI_STATS_MAX_BN) {
       *stats_fused = true;
       a.stats = stats;
+      a.fin = fin;
       switch (KC) {
         case 64: return launch_conv_tc2<64, true>(tmA, tmB, a, st);
         case 32: return launch_conv_tc2<32, true>(tmA, tmB, a, st);
@@ -604,7 +610,8 @@ static TapTable fprop_taps(int N, int C, int R, int S, int stride, int pad) {
 static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bias,
                              const void* residual, void* y, int N, int H, int W, int C, int K,
                              int R, int S, int stride, int pad, int algo, void* ws,
-                             size_t ws_bytes, b200_stream_t stream, double* stats, bool* stats_fused) {
+                             size_t ws_bytes, b200_stream_t stream, double* stats, bool* stats_fused,
+                             const EpiStatsFinal* fin = nullptr) {
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -625,7 +632,7 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
     return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, stats,
-                       stats_fused);
+                       stats_fused, fin);
   }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {
@@ -647,7 +654,7 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
   }
   TapTable tt = fprop_taps(N, C, R, S, stride, pad);
   return run_conv_tc(act, Nact, Ha, Wa, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, stats,
-                     stats_fused);
+                     stats_fused, fin);
 }
 
 extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
@@ -656,7 +663,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
                                  size_t ws_bytes, b200_stream_t stream) {
   bool fused = false;
   return conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
-                           ws_bytes, stream, nullptr, &fused);
+                           ws_bytes, stream, nullptr, &fused, nullptr);
 }
 
 static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t ws_bytes, int finalize,
@@ -666,19 +673,25 @@ static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t w
 extern "C" int b200_conv2d_fprop_stats(const void* x, const void* w_krsc, const float* bias,
                                        const void* residual, void* y, int N, int H, int W, int C, int K,
                                        int R, int S, int stride, int pad, int algo, void* ws,
-                                       size_t ws_bytes, void* stats_ws, size_t stats_ws_bytes,
-                                       b200_stream_t stream) {
+                                       size_t ws_bytes, void* stats_ws, size_t stats_ws_bytes, float eps,
+                                       float* mean, float* invstd, b200_stream_t stream) {
   B200_REQUIRE(stats_ws && K % 8 == 0, "conv2d_fprop_stats: needs a statistics workspace and K %% 8 == 0");
   B200_REQUIRE(stats_ws_bytes >= b200_bn_workspace_bytes(0, K), "conv2d_fprop_stats: statistics workspace too small");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(stats_ws) & 7) == 0, "conv2d_fprop_stats: statistics workspace must be 8-byte aligned");
+  B200_REQUIRE((mean == nullptr) == (invstd == nullptr), "conv2d_fprop_stats: mean and invstd go together");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  double* accum = reinterpret_cast<double*>(stats_ws);
+  EpiStatsFinal fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.ticket = reinterpret_cast<unsigned int*>(accum + BN_SLOTS * bn_slot_stride(K));
+  fin.mean = mean; fin.invstd = invstd; fin.eps = eps; fin.rows = (long long)N * P * Q;
   bool fused = false;
   if (int rc = conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
-                                 ws_bytes, stream, reinterpret_cast<double*>(stats_ws), &fused))
+                                 ws_bytes, stream, accum, &fused, &fin))
     return rc;
   if (fused) return 0;
-  // kernels without the fused epilogue (direct, single-CTA): one accumulate-only pass over y
-  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
-  return bn_sums_launch(y, (int64_t)N * P * Q, K, stats_ws, stats_ws_bytes, 0, 0.f, 0.f, nullptr, nullptr,
+  // kernels without the fused epilogue (direct, single-CTA): one reduction pass over y
+  return bn_sums_launch(y, (int64_t)N * P * Q, K, stats_ws, stats_ws_bytes, mean ? 1 : 0, eps, 0.f, mean, invstd,
                         nullptr, nullptr, nullptr, as_stream(stream));
 }
 
@@ -1166,6 +1179,16 @@ extern "C" int b200_bn_stats_finalize(int64_t rows, int C, float eps, float mome
   return 0;
 }
 
+extern "C" int b200_bn_running_update(const float* mean, const float* invstd, int64_t rows, int C, float eps,
+                                      float momentum, float* running_mean, float* running_var,
+                                      int64_t* num_batches_tracked, b200_stream_t stream) {
+  B200_REQUIRE(mean && invstd && running_mean && running_var && rows > 0, "bn_running_update: bad arguments");
+  launch_k(bn_running_update_kernel, (unsigned)((C + 255) / 256), 256, 0, as_stream(stream), mean, invstd, eps,
+           momentum, rows, running_mean, running_var, num_batches_tracked, C);
+  B200_LAUNCH_CHECK("bn_running_update_kernel");
+  return 0;
+}
+
 static uint32_t drop_threshold(float p) {
   if (p <= 0.f) return 0;
   double t = (double)p * 65536.0 + 0.5;
@@ -1177,8 +1200,11 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
                                const float* invstd, int stat_is_var, float eps, const float* gamma,
                                const float* beta, const void* skip, int skip_mode, int skip_C,
                                int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
-                               b200_stream_t stream) {
+                               float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                               float momentum, void* mask_out, b200_stream_t stream) {
   B200_REQUIRE(x && y, "bn_act_fwd: null pointer");
+  B200_REQUIRE(!running_mean || (running_var && mean && invstd && !stat_is_var),
+               "bn_act_fwd: the running-statistics update needs batch mean / invstd");
   B200_REQUIRE(C % 8 == 0, "bn_act_fwd: C=%d must be a multiple of 8", C);
   B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "bn_act_fwd: dropout_p out of range");
   B200_REQUIRE(skip_mode == B200_SKIP_NONE || skip, "bn_act_fwd: skip_mode set without skip tensor");
@@ -1196,6 +1222,9 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
   a.seed_offset = seed_offset;
+  a.running_mean = running_mean; a.running_var = running_var; a.num_batches_tracked = num_batches_tracked;
+  a.momentum = momentum;
+  a.mask_out = reinterpret_cast<uint8_t*>(mask_out);
   {
     const int CG = C / 8;
     const int64_t rows = (int64_t)N * H * W;
@@ -1213,17 +1242,19 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   return 0;
 }
 
-extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, void* dx, void* dskip,
-                               const void* addend, int64_t rows, int C, const float* mean,
+extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, const void* x, void* dx,
+                               void* dskip, const void* addend, int64_t rows, int C, const float* mean,
                                const float* invstd, const float* gamma, float* dgamma, float* dbeta,
                                int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
                                void* ws, size_t ws_bytes, b200_stream_t stream) {
   B200_REQUIRE(dy && dx, "bn_act_bwd: null pointer");
   B200_REQUIRE(C % 8 == 0, "bn_act_bwd: C=%d must be a multiple of 8", C);
-  B200_REQUIRE(!relu || y, "bn_act_bwd: relu mask needs the forward output y");
+  const bool gate_x = mask != nullptr;   // bit mask written by the forward: neither y nor the RNG is needed
+  B200_REQUIRE(!relu || y || mask, "bn_act_bwd: relu needs the forward's mask bytes or its output y");
   cudaStream_t st = as_stream(stream);
   BnActBwdArgs a;
   a.dy = (const bf16*)dy; a.y = (const bf16*)y; a.x = (const bf16*)x;
+  a.mask = reinterpret_cast<const uint8_t*>(mask);
   a.dx = (bf16*)dx; a.dskip = (bf16*)dskip; a.addend = (const bf16*)addend;
   a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.dgamma = dgamma; a.dbeta = dbeta;
   a.rows = rows; a.C = C; a.relu = relu;
@@ -1238,16 +1269,19 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* x, voi
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_act_bwd: workspace must be 8-byte aligned");
     static const int rbps = std::max(1, env_int("B200_BN_REDUCE_BPS", 3));
     const int CG = C / 8;
-    dim3 grid(bn_blocks(rows, C, rbps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
+    dim3 grid(bn_blocks(rows, C, rbps, gate_x ? 4 : 2), (CG + EW_THREADS - 1) / EW_THREADS);
     double* accum = reinterpret_cast<double*>(ws);
-    launch_k(bn_act_bwd_reduce_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, reinterpret_cast<unsigned int*>(accum + BN_SLOTS * bn_slot_stride(C)));
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(accum + BN_SLOTS * bn_slot_stride(C));
+    if (gate_x) launch_k(bn_act_bwd_reduce_kernel<true>, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, ticket);
+    else launch_k(bn_act_bwd_reduce_kernel<false>, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, ticket);
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   }
   {
     static const int abps = std::max(1, env_int("B200_BN_APPLY_BPS", 3));
     const int CG = C / 8;
     dim3 grid(bn_blocks(rows, C, abps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
-    launch_k(bn_act_bwd_apply_kernel, grid, EW_THREADS, 0, st, a);
+    if (gate_x) launch_k(bn_act_bwd_apply_kernel<true>, grid, EW_THREADS, 0, st, a);
+    else launch_k(bn_act_bwd_apply_kernel<false>, grid, EW_THREADS, 0, st, a);
   }
   B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;
@@ -1282,6 +1316,11 @@ extern "C" int b200_avgpool_fwd(const void* x, void* y, int N, int H, int W, int
                                 int pad, b200_stream_t stream) {
   B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "avgpool_fwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  if (pad == 0 && k == H && k == W) {   // global pooling
+    launch_k(avgpool_global_kernel, (unsigned)N, EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, H * W, C);
+    B200_LAUNCH_CHECK("avgpool_global_kernel");
+    return 0;
+  }
   launch_k(avgpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, d);
   B200_LAUNCH_CHECK("avgpool_fwd_kernel");
   return 0;

@@ -142,13 +142,22 @@ __global__ void conv_dbias_kernel(const bf16* __restrict__ dy, float* __restrict
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int cgi = cgb + cg;
     if (rl < RP && cgi < CG) {
-      for (size_t pix = p0 + rl; pix < p1; pix += RP) {
-        Vec8 v;
-        v.raw = ldg_stream(dy + pix * K + (size_t)cgi * 8);
-        float f[8];
-        v.to_float(f);
+      // 8 independent 16-byte loads in flight per thread (one per iteration ran at ~1 TB/s: 45.9 us for 42 MB)
+      for (size_t pix = p0 + rl; pix < p1; pix += 8 * (size_t)RP) {
+        Vec8 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        for (int u = 0; u < 8; ++u) {
+          const size_t pu = pix + (size_t)u * RP;
+          v[u].raw = make_uint4(0u, 0u, 0u, 0u);
+          if (pu < p1) v[u].raw = ldg_stream(dy + pu * K + (size_t)cgi * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float f[8];
+          v[u].to_float(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
       }
     }
 #pragma unroll

@@ -60,6 +60,7 @@ struct ConvTcArgs {
   const bf16* residual;
   const float* bias;
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
+  EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -112,6 +113,25 @@ __device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, in
     atomicAdd(dst + (size_t)(i & 1) * C + (i >> 1), (double)v);
   }
   epi_bar();
+}
+
+// after the last tile of a CTA: the CTA that finishes last turns the accumulated sums into mean / invstd
+// (the finalize step of the following batch norm; saves one launch per BN layer) and clears them
+__device__ __forceinline__ void epi_stats_finalize(const EpiStatsFinal& fin, double* accum, int C, int e) {
+  __shared__ int s_last;
+  if (fin.mean == nullptr) return;
+  // every epilogue thread of this CTA has issued its atomics (epi_stats_flush ends with a barrier)
+  if (e == 0) {
+    __threadfence();
+    s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1u) ? 1 : 0;
+    __threadfence();
+  }
+  epi_bar();
+  if (s_last) {
+    for (int c = e; c < C; c += TC2_EPI_THREADS)
+      stats_to_mean_invstd(accum, C, c, fin.rows, fin.eps, fin.mean, fin.invstd);
+    if (e == 0) *fin.ticket = 0u;
+  }
 }
 
 template <int KC>
@@ -532,6 +552,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
+    if (STATS) epi_stats_finalize(args.fin, args.stats, args.ldo, e);
   }
 
   __syncwarp();
@@ -573,6 +594,7 @@ struct ConvHaloArgs {
   const bf16* residual;
   const float* bias;
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
+  EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
 };
 
 // MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
@@ -802,6 +824,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, e);
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
+    if (STATS) epi_stats_finalize(args.fin, args.stats, args.ldo, e);
   }
 
   __syncwarp();

@@ -11,9 +11,11 @@ constexpr int EW_THREADS = 256;
 
 // Inverted dropout on the 8 values of vector `v`: element j is dropped when its 16-bit uniform is
 // below drop_thr, else scaled by 1/(1-p) and (ROUND) rounded to bf16 like the reference's bf16 multiply.
+// Returns the keep mask (bit j set = element j kept).
 template <bool ROUND>
-__device__ __forceinline__ void dropout8(float* f, uint64_t seed, size_t v, uint32_t drop_thr,
-                                         float inv_keep) {
+__device__ __forceinline__ uint32_t dropout8(float* f, uint64_t seed, size_t v, uint32_t drop_thr,
+                                             float inv_keep) {
+  uint32_t keep = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const uint2 d = rng_draw4(seed, (uint64_t)v * 2 + h);
@@ -21,9 +23,12 @@ __device__ __forceinline__ void dropout8(float* f, uint64_t seed, size_t v, uint
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float t = f[4 * h + j] * inv_keep;
-      f[4 * h + j] = (u[j] < drop_thr) ? 0.f : (ROUND ? round_bf16(t) : t);
+      const bool k = u[j] >= drop_thr;
+      keep |= (k ? 1u : 0u) << (4 * h + j);
+      f[4 * h + j] = k ? (ROUND ? round_bf16(t) : t) : 0.f;
     }
   }
+  return keep;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -70,21 +75,6 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
   return is_last != 0;
 }
 
-// sum of accumulator `a` of channel c over the slots; clears them
-__device__ __forceinline__ double drain_slots(double* accum, int C, int a, int c) {
-  const size_t stride = bn_slot_stride(C);
-  double v[BN_SLOTS];
-#pragma unroll
-  for (int k = 0; k < BN_SLOTS; ++k) v[k] = __ldcg(accum + k * stride + (size_t)a * C + c);
-  double s = 0.0;
-#pragma unroll
-  for (int k = 0; k < BN_SLOTS; ++k) {
-    s += v[k];
-    accum[k * stride + (size_t)a * C + c] = 0.0;
-  }
-  return s;
-}
-
 // geometry shared by the reduction kernels: blockIdx.y selects a chunk of <=256 channel groups
 struct ReduceGeom {
   int CG;    // C / 8
@@ -119,6 +109,19 @@ struct BnStatsArgs {
   int finalize;           // 0: accumulate only (the sums are finalized by bn_stats_finalize_kernel)
 };
 
+// running statistics of one channel from its batch mean / invstd (torch.nn.BatchNorm2d: momentum update with
+// the UNBIASED batch variance). The biased variance is recovered as 1/invstd^2 - eps.
+__device__ __forceinline__ void bn_running_update_channel(float mean, float invstd, float eps, float momentum,
+                                                          int64_t rows, float* running_mean, float* running_var,
+                                                          int c) {
+  const double is = (double)invstd;
+  double var = 1.0 / (is * is) - (double)eps;
+  if (var < 0.0) var = 0.0;
+  const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+}
+
 // one channel: drain the accumulator slots, write mean / invstd, update the running statistics
 __device__ __forceinline__ void bn_finalize_channel(const BnStatsArgs& a, int c) {
   const int C = a.C;
@@ -133,6 +136,16 @@ __device__ __forceinline__ void bn_finalize_channel(const BnStatsArgs& a, int c)
     a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)m;
     a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
   }
+}
+
+// running statistics from mean / invstd that a conv kernel's tail produced (compatibility path: the
+// training forward folds this update into bn_act_fwd)
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                         float eps, float momentum, int64_t rows, float* running_mean,
+                                         float* running_var, int64_t* num_batches_tracked, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_running_update_channel(mean[c], invstd[c], eps, momentum, rows, running_mean, running_var, c);
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
 // Batch statistics in ONE launch: every block adds its per-channel sum / sum of squares to the fp64
@@ -207,6 +220,15 @@ struct BnActFwdArgs {
   uint32_t drop_thr;  // drop when u16 < drop_thr
   uint64_t seed;
   const uint64_t* seed_offset;  // device step counter folded into the seed (CUDA-graph replays)
+  // optional: running-statistics update of the batch norm whose mean / invstd came out of a conv kernel's
+  // tail (done by the blocks with blockIdx.x == 0, one thread per 8-channel group)
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum;
+  // optional: one byte per (pixel, 8-channel group); bit j = unit j passed the ReLU gate AND was kept by the
+  // dropout. The backward kernels read this instead of y (1/16 of the bytes) and regenerate nothing.
+  uint8_t* mask_out;
 };
 
 // Thread mapping of the element-wise BN kernels: a thread owns ONE 8-channel group for the whole
@@ -229,6 +251,15 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnAc
     }
   }
   const int64_t rows = (int64_t)a.N * a.H * a.W;
+  if (a.running_mean && blockIdx.x == 0 && g.rl == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cgi * 8 + j;
+      bn_running_update_channel(a.mean[c], a.invstd[c], a.eps, a.momentum, rows, a.running_mean,
+                                a.running_var, c);
+    }
+    if (cgi == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
+  }
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   const bool skip_here = SKIP && (a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C));
   const int64_t stride = (int64_t)g.RP * gridDim.x;
@@ -270,11 +301,16 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnAc
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + sk[j]);
       }
+      uint32_t bits = 0xffu;
       if (a.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        for (int j = 0; j < 8; ++j) {
+          if (!(f[j] > 0.f)) bits &= ~(1u << j);
+          f[j] = fmaxf(f[j], 0.f);
+        }
       }
-      if (a.drop_thr) dropout8<false>(f, seed, v, a.drop_thr, a.inv_keep);  // the pack below rounds
+      if (a.drop_thr) bits &= dropout8<false>(f, seed, v, a.drop_thr, a.inv_keep);  // the pack below rounds
+      if (a.mask_out) a.mask_out[v] = (uint8_t)bits;
       Vec8 o;
       o.from_float(f);
       stg_stream(a.y + v * 8, o.raw);
@@ -288,6 +324,7 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnAc
 struct BnActBwdArgs {
   const bf16* dy;
   const bf16* y;
+  const uint8_t* mask;
   const bf16* x;
   bf16* dx;
   bf16* dskip;
@@ -306,13 +343,25 @@ struct BnActBwdArgs {
   const uint64_t* seed_offset;
 };
 
-// g = dy * mask / (1-p). With a fused ReLU the saved forward output y is non-zero exactly where the unit
-// was both active and kept, so (y != 0) is the combined ReLU + dropout mask and no random numbers are
-// regenerated; without ReLU the dropout mask is regenerated from the counter RNG.
-__device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t seed, size_t v,
-                                                 const Vec8& dv, const Vec8& yv, float* g) {
+// g = dy * mask / (1-p), mask = ReLU gate AND dropout keep.
+//   BITS = true : the forward stored the combined mask as one byte per 8-channel group (bn_act_fwd mask_out):
+//                 0.125 B/element instead of the 2 B/element of y, and no random numbers are regenerated
+//                 (ncu, round 1: both backward kernels read 126 MB for a 42 MB tensor: dy, x and y);
+//   BITS = false: with a fused ReLU the saved forward output y is non-zero exactly where the unit was both
+//                 active and kept; without ReLU the dropout mask is regenerated from the counter RNG.
+template <bool BITS>
+__device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t seed, size_t v, const Vec8& dv,
+                                                 const Vec8& yv, uint32_t bits, float* g) {
   dv.to_float(g);
-  if (a.relu) {
+  if (BITS) {
+    if (a.drop_thr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? round_bf16(g[j] * a.inv_keep) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
+    }
+  } else if (a.relu) {
     float yf[8];
     yv.to_float(yf);
     if (a.drop_thr) {
@@ -327,7 +376,9 @@ __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t
   }
 }
 
-// accum[0][c] += sum g, accum[1][c] += sum g * xhat; the last block writes dbeta / dgamma and clears accum
+// accum[0][c] += sum g, accum[1][c] += sum g * x; the last block writes dbeta = sum g and
+// dgamma = invstd * (sum g*x - mean * sum g) (= sum g * xhat, finished in fp64) and clears accum
+template <bool BITS>
 __global__ void __launch_bounds__(EW_THREADS, 3)
 bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsigned int* ticket) {
   extern __shared__ float red_smem[];
@@ -338,26 +389,22 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
   const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
   if (g.active) {
     const int cgi = g.cg0 + g.cgl;
-    float mu[8], is[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mu[j] = a.mean[cgi * 8 + j];
-      is[j] = a.invstd[cgi * 8 + j];
-    }
-    constexpr int U = 2;
+    constexpr int U = BITS ? 4 : 2;
     const int64_t batch = (int64_t)g.RP * U;
     const int64_t rows_per_block = ((a.rows + gridDim.x - 1) / gridDim.x + batch - 1) / batch * batch;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(a.rows, r0 + rows_per_block);
     for (int64_t rb = r0 + g.rl; rb < r1; rb += U * (int64_t)g.RP) {
-      Vec8 dv[U], yv[U], xv[U];
+      Vec8 dv[U], yv[BITS ? 1 : U], xv[U];
+      uint32_t mb[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t r = rb + u * (int64_t)g.RP;
         if (r < r1) {
           const size_t v = (size_t)r * g.CG + cgi;
           dv[u].raw = ldg_stream(a.dy + v * 8);
-          if (a.relu) yv[u].raw = ldg_stream(a.y + v * 8);
+          if (BITS) mb[u] = __ldg(a.mask + v);
+          else if (a.relu) yv[BITS ? 0 : u].raw = ldg_stream(a.y + v * 8);
           xv[u].raw = ldg_stream(a.x + v * 8);
         }
       }
@@ -367,12 +414,12 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
         if (r >= r1) break;
         const size_t v = (size_t)r * g.CG + cgi;
         float gr[8], xf[8];
-        masked_grad_from(a, seed, v, dv[u], yv[u], gr);
         xv[u].to_float(xf);
+        masked_grad_from<BITS>(a, seed, v, dv[u], yv[BITS ? 0 : u], BITS ? mb[u] : 0u, gr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[j] += gr[j];
-          acc[8 + j] = fmaf(gr[j], (xf[j] - mu[j]) * is[j], acc[8 + j]);
+          acc[8 + j] = fmaf(gr[j], xf[j], acc[8 + j]);
         }
       }
     }
@@ -380,8 +427,9 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
   block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, accum, a.C, g.cg0 * 8);
   if (!last_block_done(ticket)) return;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    a.dbeta[c] = (float)drain_slots(accum, a.C, 0, c);
-    a.dgamma[c] = (float)drain_slots(accum, a.C, 1, c);
+    const double s0 = drain_slots(accum, a.C, 0, c), s1 = drain_slots(accum, a.C, 1, c);
+    a.dbeta[c] = (float)s0;
+    a.dgamma[c] = (float)((double)a.invstd[c] * (s1 - (double)a.mean[c] * s0));
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -389,6 +437,7 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
 // dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g.
 // Per channel this is dx = k1 * g + k2 * x + k3 with
 //   k1 = gamma*invstd, k2 = -k1*invstd*dgamma/rows, k3 = -k1*dbeta/rows - k2*mean   (registers).
+template <bool BITS>
 __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
@@ -410,14 +459,16 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const B
   const int64_t stride = (int64_t)g.RP * gridDim.x;
   constexpr int U = 2;
   for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < a.rows; r0 += U * stride) {
-    Vec8 dv[U], yv[U], xv[U], av[U];
+    Vec8 dv[U], yv[BITS ? 1 : U], xv[U], av[U];
+    uint32_t mb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = r0 + u * stride;
       if (r < a.rows) {
         const size_t v = (size_t)r * g.CG + cgi;
         dv[u].raw = ldg_stream(a.dy + v * 8);
-        if (a.relu) yv[u].raw = ldg_stream(a.y + v * 8);
+        if (BITS) mb[u] = __ldg(a.mask + v);
+        else if (a.relu) yv[BITS ? 0 : u].raw = ldg_stream(a.y + v * 8);
         if (a.affine) xv[u].raw = ldg_stream(a.x + v * 8);
         if (a.addend) av[u].raw = ldg_stream(a.addend + v * 8);
       }
@@ -427,16 +478,15 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const B
       const int64_t r = r0 + u * stride;
       if (r >= a.rows) break;
       const size_t v = (size_t)r * g.CG + cgi;
-      float gr[8], d[8];
-      masked_grad_from(a, seed, v, dv[u], yv[u], gr);
+      float gr[8], d[8], xf[8];
+      if (a.affine) xv[u].to_float(xf);
+      masked_grad_from<BITS>(a, seed, v, dv[u], yv[BITS ? 0 : u], BITS ? mb[u] : 0u, gr);
       if (a.dskip) {
         Vec8 o;
         o.from_float(gr);
         stg_stream(a.dskip + v * 8, o.raw);
       }
       if (a.affine) {
-        float xf[8];
-        xv[u].to_float(xf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = round_bf16(fmaf(k1[j], gr[j], fmaf(k2[j], xf[j], k3[j])));
       } else {
@@ -725,6 +775,60 @@ __global__ void avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
     Vec8 o;
     o.from_float(acc);
     stg_stream(y + v * 8, o.raw);
+  }
+}
+
+// Global average pooling (k == H == W, pad 0: the `ap8,1,0` head of the CIFAR nets): one block per image,
+// thread = (8-channel group, pixel lane), 4 independent 16-byte loads in flight per thread, shared-memory
+// reduction over the pixel lanes. (The generic kernel walks the 64 pixels serially in one thread: 39.6 us
+// for the 10 MB WRN tensor in round 1.)
+__global__ void __launch_bounds__(EW_THREADS) avgpool_global_kernel(const bf16* __restrict__ x,
+                                                                    bf16* __restrict__ y, int HW, int C) {
+  __shared__ float red[EW_THREADS * 8];
+  const int CG = C / 8;
+  const int CGb = min(EW_THREADS, CG);
+  const int RP = EW_THREADS / CGb;
+  const int cgl = threadIdx.x % CGb, part = threadIdx.x / CGb;
+  const int n = blockIdx.x;
+  const float inv = 1.f / (float)HW;
+  for (int cg0 = 0; cg0 < CG; cg0 += CGb) {
+    const int cg = cg0 + cgl;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (part < RP && cg < CG) {
+      const bf16* base = x + (size_t)n * HW * C + (size_t)cg * 8;
+      for (int p = part; p < HW; p += 4 * RP) {
+        Vec8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u].raw = make_uint4(0u, 0u, 0u, 0u);
+          if (p + u * RP < HW) v[u].raw = ldg_stream(base + (size_t)(p + u * RP) * C);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          v[u].to_float(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if (part == 0 && cg < CG) {
+      float s[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+      for (int r = 0; r < RP; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += red[(r * CGb + cgl) * 8 + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] *= inv;
+      Vec8 o;
+      o.from_float(s);
+      *reinterpret_cast<uint4*>(y + (size_t)n * C + (size_t)cg * 8) = o.raw;
+    }
+    __syncthreads();
   }
 }
 

@@ -44,6 +44,7 @@ __global__ void linear_bwd_dw_kernel(const bf16* __restrict__ dy, const bf16* __
   if (idx >= (size_t)O * I) return;
   const int o = (int)(idx / I), i = (int)(idx % I);
   float acc = 0.f, accb = 0.f;
+#pragma unroll 8
   for (int b = 0; b < B; ++b) {
     const float g = __bfloat162float(dy[(size_t)b * O + o]);
     acc = fmaf(g, __bfloat162float(x[(size_t)b * I + i]), acc);

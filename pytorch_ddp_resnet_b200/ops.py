@@ -48,9 +48,10 @@ def bn_accumulators(device: torch.device, nbytes: int = 0) -> torch.Tensor:
     return t
 
 
-# Fused conv + BN statistics: conv_fprop(want_stats=True) leaves the per-channel sums of its output in the
-# accumulators and records (output pointer, rows, C) here; the bn_stats call that follows on the SAME tensor
-# only finalizes them. Anything else that needs the accumulators first clears an unconsumed record.
+# Fused conv + BN statistics: conv_fprop(want_stats=True) sums its output per channel in the epilogue, and the
+# CTA that finishes last turns the sums into mean / invstd (and clears the accumulators). The record
+# (output pointer, rows, C, eps, mean, invstd) is kept here; the batch-norm statistics call that follows on
+# the SAME tensor takes mean / invstd from it without launching anything. An unconsumed record is simply dropped.
 _pending_stats = {}
 
 
@@ -59,9 +60,7 @@ def _accum_key(device: torch.device):
 
 
 def _drop_pending_stats(device: torch.device) -> None:
-    rec = _pending_stats.pop(_accum_key(device), None)
-    if rec is not None:
-        rec[3].zero_()   # sums nobody consumed (e.g. a conv that is not followed by a batch norm)
+    _pending_stats.pop(_accum_key(device), None)
 
 
 def fused_bn_stats_enabled() -> bool:
@@ -152,8 +151,9 @@ def _out_hw(H, W, R, S, stride, pad):
 
 
 def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=None,
-               want_stats: bool = False):
-    """want_stats: also accumulate the batch-norm sums of the output (consumed by the next bn_stats(y))."""
+               want_stats: bool = False, eps: float = 1e-5):
+    """want_stats: also compute the batch-norm statistics (mean, invstd with `eps`) of the output in the conv
+    kernel itself; the next bn_batch_stats(y) / bn_stats(y) picks them up."""
     _check_act(x, "conv_fprop.x")
     N, H, W, C = x.shape
     K, R, S, Cw = w_krsc.shape
@@ -170,10 +170,12 @@ def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=
         _drop_pending_stats(x.device)
         nacc = _lib.load().b200_bn_workspace_bytes(N * P * Q, K)
         acc = bn_accumulators(x.device, nacc)
+        mean = torch.empty((K,), dtype=torch.float32, device=x.device)
+        invstd = torch.empty((K,), dtype=torch.float32, device=x.device)
         _lib.call("b200_conv2d_fprop_stats", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
                   y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, acc.data_ptr(),
-                  acc.numel() * 8, _stream())
-        _pending_stats[_accum_key(x.device)] = (y.data_ptr(), N * P * Q, K, acc)
+                  acc.numel() * 8, float(eps), mean.data_ptr(), invstd.data_ptr(), _stream())
+        _pending_stats[_accum_key(x.device)] = (y.data_ptr(), N * P * Q, K, float(eps), mean, invstd)
         return y
     _lib.call("b200_conv2d_fprop", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
               y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
@@ -288,35 +290,49 @@ def conv_tc_supported(pass_: int, N, H, W, C, K, R, S, stride, pad) -> bool:
 # --------------------------------------------------------------------------------------------------
 # batch norm / activation / dropout / skip
 # --------------------------------------------------------------------------------------------------
-def bn_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_var=None,
-             num_batches_tracked=None):
-    """Batch statistics of an [..., C] bf16 tensor -> (mean, invstd); updates running stats in place."""
+def bn_batch_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_var=None,
+                   num_batches_tracked=None):
+    """Batch statistics of an [..., C] bf16 tensor -> (mean, invstd, deferred).
+    deferred = False: one reduction launch computed them and updated the running statistics in place.
+    deferred = True : the conv that produced x already computed them (conv_fprop(want_stats=True)); nothing
+    was launched and the running statistics have NOT been updated: pass them to bn_act_fwd(running=...)."""
     _check_act(x, "bn_stats.x")
     C = x.shape[-1]
     rows = x.numel() // C
+    rec = _pending_stats.pop(_accum_key(x.device), None)
+    if rec is not None and rec[:4] == (x.data_ptr(), rows, C, float(eps)):
+        return rec[4], rec[5], True
     mean = torch.empty((C,), dtype=torch.float32, device=x.device)
     invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
     nws = _lib.load().b200_bn_workspace_bytes(rows, C)
-    rec = _pending_stats.pop(_accum_key(x.device), None)
-    if rec is not None:
-        if rec[:3] == (x.data_ptr(), rows, C):   # the conv that produced x already summed it
-            _lib.call("b200_bn_stats_finalize", rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
-                      _p(running_mean), _p(running_var), _p(num_batches_tracked), rec[3].data_ptr(),
-                      rec[3].numel() * 8, _stream())
-            return mean, invstd
-        rec[3].zero_()
     ws = bn_accumulators(x.device, nws)
     _lib.call("b200_bn_stats", x.data_ptr(), rows, C, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
               _p(running_mean), _p(running_var), _p(num_batches_tracked), ws.data_ptr(), nws, _stream())
+    return mean, invstd, False
+
+
+def bn_stats(x, eps: float, momentum: float = 0.1, running_mean=None, running_var=None,
+             num_batches_tracked=None):
+    """Batch statistics of an [..., C] bf16 tensor -> (mean, invstd); updates running stats in place."""
+    mean, invstd, deferred = bn_batch_stats(x, eps, momentum, running_mean, running_var, num_batches_tracked)
+    if deferred and running_mean is not None:
+        C = x.shape[-1]
+        _lib.call("b200_bn_running_update", mean.data_ptr(), invstd.data_ptr(), x.numel() // C, C, eps, momentum,
+                  running_mean.data_ptr(), running_var.data_ptr(), _p(num_batches_tracked), _stream())
     return mean, invstd
 
 
 def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var: bool = False,
                eps: float = 1e-5, skip=None, skip_mode: int = _lib.SKIP_NONE, relu: bool = True,
-               dropout_p: float = 0.0, seed: int = 0):
+               dropout_p: float = 0.0, seed: int = 0, running=None, want_mask: bool = False):
+    """running: optional (running_mean, running_var, num_batches_tracked, momentum) updated from mean / invstd
+    by the same launch (statistics that came out of a conv kernel: bn_batch_stats(...)[2] is True).
+    want_mask: also return the ReLU/dropout bit mask (uint8 [N,H,W,C/8]) for bn_act_bwd -> (y, mask)."""
     _check_act(x, "bn_act_fwd.x")
     N, H, W, C = x.shape
     y = torch.empty_like(x)
+    mask = torch.empty((N, H, W, C // 8), dtype=torch.uint8, device=x.device) if want_mask else None
+    rm, rv, nbt, mom = running if running is not None else (None, None, None, 0.0)
     skip_C = 0
     if skip is not None:
         _check_act(skip, "bn_act_fwd.skip")
@@ -328,14 +344,16 @@ def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var:
     _lib.call("b200_bn_act_fwd", x.data_ptr(), y.data_ptr(), N, H, W, C, _p(mean), _p(invstd),
               int(stat_is_var), eps, _p(gamma), _p(beta), _p(skip), skip_mode if skip is not None else 0,
               skip_C, int(relu), float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
-              step_counter(x.device).data_ptr() if dropout_p > 0 else None, _stream())
-    return y
+              step_counter(x.device).data_ptr() if dropout_p > 0 else None, _p(rm), _p(rv), _p(nbt), float(mom),
+              _p(mask), _stream())
+    return (y, mask) if want_mask else y
 
 
 def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = True,
                dropout_p: float = 0.0, seed: int = 0, addend=None, want_dskip: bool = False,
-               out_dgamma=None, out_dbeta=None):
-    """Returns (dx, dgamma, dbeta, dskip). out_dgamma / out_dbeta: optional fp32 [C] destinations."""
+               out_dgamma=None, out_dbeta=None, mask=None):
+    """Returns (dx, dgamma, dbeta, dskip). out_dgamma / out_dbeta: optional fp32 [C] destinations.
+    mask: the uint8 bit mask of bn_act_fwd(want_mask=True); with it y may be None."""
     _check_act(dy, "bn_act_bwd.dy")
     C = dy.shape[-1]
     rows = dy.numel() // C
@@ -353,7 +371,9 @@ def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = Tru
     if addend is not None:
         _check_act(addend, "bn_act_bwd.addend")
         assert addend.shape == dy.shape
-    _lib.call("b200_bn_act_bwd", dy.data_ptr(), _p(y), _p(x), dx.data_ptr(), _p(dskip), _p(addend), rows,
+    if mask is not None:
+        assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() * 8 == dy.numel()
+    _lib.call("b200_bn_act_bwd", dy.data_ptr(), _p(y), _p(mask), _p(x), dx.data_ptr(), _p(dskip), _p(addend), rows,
               C, _p(mean), _p(invstd), _p(gamma), _p(dgamma), _p(dbeta), int(relu), float(dropout_p),
               int(seed) & 0xFFFFFFFFFFFFFFFF,
               step_counter(dy.device).data_ptr() if dropout_p > 0 else None, _p(ws), nws, _stream())

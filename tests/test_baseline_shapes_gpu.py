@@ -156,6 +156,13 @@ def test_bn_relu_dropout_fwd_bwd_at_baseline_shapes(C, HW):
     dx_ref = gamma * invstd * (gg - (db_ref + xhat * dg_ref) / rows)
     assert rel_l2(dbeta, db_ref) < 1e-3 and rel_l2(dgamma, dg_ref) < 1e-3
     assert rel_l2(dx, dx_ref) < 4e-3
+    # the bit-mask path (what the blocks use: 0.125 B/element instead of re-reading y) gives the same result
+    ym, mask = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, want_mask=True)
+    assert torch.equal(ym, y)
+    bits = ((mask.unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).reshape(y.shape)
+    assert torch.equal(bits.bool(), y != 0)
+    dxm, dgm, dbm, _ = ops.bn_act_bwd(dy, None, x, mean, invstd, gamma, relu=True, mask=mask)
+    assert rel_l2(dbm, dbeta) < 1e-6 and rel_l2(dgm, dgamma) < 1e-5 and rel_l2(dxm, dx) < 1e-4
     # ---- dropout 0.3 -------------------------------------------------------------------------------
     p = 0.3
     yd = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=p, seed=1234)
@@ -169,7 +176,12 @@ def test_bn_relu_dropout_fwd_bwd_at_baseline_shapes(C, HW):
     assert (per_channel - (1 - p)).abs().max() < 0.05
     yd2 = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=p, seed=1235)
     assert (yd2 != yd).any()
-    dxd, dgd, dbd, _ = ops.bn_act_bwd(dy, yd, x, mean, invstd, gamma, relu=True, dropout_p=p, seed=1234)
+    ydm, maskd = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=p, seed=1234, want_mask=True)
+    assert torch.equal(ydm, yd)
+    bitsd = ((maskd.unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).reshape(y.shape)
+    assert torch.equal(bitsd.bool(), kept)
+    dxd, dgd, dbd, _ = ops.bn_act_bwd(dy, None, x, mean, invstd, gamma, relu=True, dropout_p=p, seed=1234,
+                                      mask=maskd)
     ggd = (dy.float() * (1 / (1 - p))).bfloat16().float() * kept.float()
     dbd_ref = ggd.reshape(-1, C).sum(0)
     dgd_ref = (ggd * xhat).reshape(-1, C).sum(0)

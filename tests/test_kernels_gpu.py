@@ -193,6 +193,48 @@ def test_unconsumed_fused_statistics_are_discarded():
     assert rel_l2(g[2], gref) <= 1e-4
 
 
+@pytest.mark.parametrize("skip_mode", ["none", "same", "subsample_pad"])
+def test_bn_act_mask_path_equals_y_path(skip_mode):
+    """bn_act_fwd(want_mask) + bn_act_bwd(mask=...) == the y-based backward, also when the forward added a skip
+    tensor before the ReLU (the v1-ordering block tail); deferred running statistics inside bn_act_fwd."""
+    ops, _lib = _ops()
+    N, H, W, C = 6, 8, 8, 48
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(N, H, W, C, device="cuda", generator=g).bfloat16()
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.3
+    kw = {}
+    if skip_mode == "same":
+        kw = dict(skip=torch.randn(N, H, W, C, device="cuda", generator=g).bfloat16(), skip_mode=_lib.SKIP_SAME)
+    elif skip_mode == "subsample_pad":
+        kw = dict(skip=torch.randn(N, 2 * H, 2 * W, C // 2, device="cuda", generator=g).bfloat16(),
+                  skip_mode=_lib.SKIP_SUBSAMPLE_PAD)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    mean, invstd = ops.bn_stats(x, 1e-5)
+    y = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, **kw)
+    ym, mask = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, want_mask=True,
+                              running=(rm, rv, nbt, 0.1), **kw)
+    assert torch.equal(y, ym)
+    xf = x.float().reshape(-1, C)
+    assert nbt.item() == 1
+    assert torch.allclose(rm, 0.1 * xf.mean(0), atol=1e-5, rtol=1e-4)
+    assert torch.allclose(rv, 0.9 + 0.1 * xf.var(0, unbiased=True), atol=1e-5, rtol=1e-4)
+    r1 = ops.bn_act_bwd(dy, y, x, mean, invstd, gamma, relu=True, want_dskip=True)
+    r2 = ops.bn_act_bwd(dy, None, x, mean, invstd, gamma, relu=True, want_dskip=True, mask=mask)
+    assert torch.equal(r1[3], r2[3])                       # dskip = masked dy
+    assert rel_l2(r2[2], r1[2]) < 1e-6 and rel_l2(r2[1], r1[1]) < 1e-5 and rel_l2(r2[0], r1[0]) < 1e-4
+    # dropout without ReLU (v1 ordering): the mask is the KEEP mask, also where the input is exactly zero
+    xz = torch.relu(x)
+    yd, md = ops.bn_act_fwd(xz, relu=False, dropout_p=0.4, seed=7, want_mask=True)
+    d1 = ops.bn_act_bwd(dy, None, None, relu=False, dropout_p=0.4, seed=7)[0]
+    d2 = ops.bn_act_bwd(dy, None, None, relu=False, dropout_p=0.4, seed=7, mask=md)[0]
+    assert torch.equal(d1, d2)
+    keep_frac = (d2 != 0).float().mean().item()
+    assert abs(keep_frac - 0.6) < 0.03
+
+
 def test_weight_prep():
     ops, _ = _ops()
     w = torch.randn(48, 3, 3, 40, device="cuda")

@@ -16,11 +16,15 @@ for (N, H, C) in [(128, 32, 160), (128, 16, 320), (128, 8, 640)]:
     gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
     mean, invstd = ops.bn_stats(xs[0], 1e-5)
     ays = [ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1) for x in xs]
+    mks = [ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1, want_mask=True)[1] for x in xs]
 
     cases = {
         "bn_stats":            (1, lambda i: ops.bn_stats(xs[i], 1e-5)),
         "bn_act_fwd":          (2, lambda i: ops.bn_act_fwd(xs[i], mean, invstd, gamma, beta, relu=True)),
         "bn_act_fwd_dropout":  (2, lambda i: ops.bn_act_fwd(xs[i], mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1)),
+        "bn_act_fwd_drop_mask": (2.0625, lambda i: ops.bn_act_fwd(xs[i], mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1, want_mask=True)),
+        "bn_act_bwd_mask_drop": (5.125, lambda i: ops.bn_act_bwd(dys[i], None, xs[i], mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1, mask=mks[i])),
+        "bn_act_bwd_mask_add":  (6.125, lambda i: ops.bn_act_bwd(dys[i], None, xs[i], mean, invstd, gamma, relu=True, mask=mks[i], addend=xs[(i + 1) % nset])),
         "bn_act_bwd":          (7, lambda i: ops.bn_act_bwd(dys[i], ays[i], xs[i], mean, invstd, gamma, relu=True)),
         "bn_act_bwd_dropout":  (7, lambda i: ops.bn_act_bwd(dys[i], ays[i], xs[i], mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1)),
         "bn_act_bwd_addend":   (8, lambda i: ops.bn_act_bwd(dys[i], ays[i], xs[i], mean, invstd, gamma, relu=True, addend=xs[(i + 1) % nset])),
