@@ -151,14 +151,16 @@ static CUtensorMapSwizzle swizzle_for(int inner_elems) {
 }
 
 // bf16 tensor [N][H][W][C] with box (bc, bw, bh, bn)
+// `pstride` > 1: the box takes every pstride-th pixel in w and h (TMA elementStrides): a stride-2 convolution
+// reads its taps straight from the full-resolution tensor, bw x bh pixels land densely in shared memory.
 static int make_tmap_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bc,
-                          int bw, int bh, int bn) {
+                          int bw, int bh, int bn, int pstride = 1) {
   EncodeTiledFn fn = encode_fn();
   B200_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)(bw * pstride), (cuuint32_t)(bh * pstride), (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, (cuuint32_t)pstride, (cuuint32_t)pstride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -304,9 +306,9 @@ extern "C" size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int
     const size_t kpad = im2col_kpad(R, S, C);
     return align_up((size_t)N * P * Q * kpad * 2, 1024) + align_up((size_t)K * kpad * 4, 1024);
   }
-  if (stride != 2) return 0;
+  if (stride != 2 || pass != B200_PASS_DGRAD) return 0;
   if (!b200_conv2d_tc_supported(pass, N, H, W, C, K, R, S, stride, pad)) return 0;
-  return (size_t)N * H * W * C * 2;  // parity-split copy of the full-resolution tensor
+  return (size_t)N * H * W * C * 2;  // stride-2 dgrad: the four output phases before the merge
 }
 
 static bool use_tc(int algo, int pass, int N, int H, int W, int C, int K, int R, int S, int stride,
@@ -496,7 +498,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
                        int wcols, const TapTable& taps, void* out, const void* residual,
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
                        double* stats = nullptr, bool* stats_fused = nullptr,
-                       const EpiStatsFinal* finp = nullptr) {
+                       const EpiStatsFinal* finp = nullptr, int cstride = 1) {
   EpiStatsFinal fin;
   memset(&fin, 0, sizeof(fin));
   if (finp) fin = *finp;
@@ -517,7 +519,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   //  MMA slowed the issue loop more than SWIZZLE_128B gained; KC stays a divisor of Cin)
   // halo-reuse kernel: 3x3 taps with unit displacements on an un-split input, maps that tile in 8x16
   {
-    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg;
+    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg && cstride == 1;
     for (int i = 0; unit && i < taps.n; ++i)
       unit = taps.dn[i] == 0 && taps.dh[i] >= -1 && taps.dh[i] <= 1 && taps.dw[i] >= -1 && taps.dw[i] <= 1;
     const int mt8x16 = (Q / 8) * (P / 16) * Nimg;
@@ -547,15 +549,16 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
   a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles;
   a.taps = taps;
-  if (const char* e = getenv("B200_PROBE_ROWOFF")) a.probe_rowoff = atoi(e);
-  if (const char* e = getenv("B200_PROBE_BASEOFF")) a.probe_baseoff = atoi(e);
+  a.cstride = cstride;
+  B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
+               "conv_tc: strided TMA box exceeds 256 elements");
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
   if (pair) {
     // SM pair: every CTA stages BN/2 filter rows (whole 8-row swizzle atoms, UMMA N multiple of 16)
     CUtensorMap tmA, tmB;
-    if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
+    if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn, cstride)) return rc;
     if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
     if (stats && BN <= EPI_STATS_MAX_BN) {
       *stats_fused = true;
@@ -579,7 +582,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   const int m_tiles = t.tiles_w * t.tiles_h * t.tiles_n;
   while (cs > 1 && (m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0)) cs /= 2;
   CUtensorMap tmA, tmB;
-  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn)) return rc;
+  if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn, cstride)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / cs)) return rc;
   switch (KC) {
     case 64: return launch_conv_tc_cs<64>(cs, tmA, tmB, a, st);
@@ -589,19 +592,14 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
 }
 
 // taps of fprop / wgrad (window displacement on the input, column in the KRSC filter matrix)
-static TapTable fprop_taps(int N, int C, int R, int S, int stride, int pad) {
+// (for stride 2 the window origin is 2 * output pixel + displacement and the TMA map skips every other pixel)
+static TapTable fprop_taps(int C, int R, int S, int pad) {
   TapTable tt;
   memset(&tt, 0, sizeof(tt));
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       const int i = tt.n++;
-      const int eh = r - pad, ew = s - pad;
-      if (stride == 1) {
-        tt.dh[i] = eh; tt.dw[i] = ew; tt.dn[i] = 0;
-      } else {
-        tt.dh[i] = floordiv2(eh); tt.dw[i] = floordiv2(ew);
-        tt.dn[i] = (mod2(eh) * 2 + mod2(ew)) * N;
-      }
+      tt.dh[i] = r - pad; tt.dw[i] = s - pad; tt.dn[i] = 0;
       tt.wcol[i] = (r * S + s) * C;
     }
   return tt;
@@ -642,19 +640,11 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
     B200_LAUNCH_CHECK("conv_fprop_direct_kernel");
     return 0;
   }
-  const void* act = x;
-  int Nact = N, Ha = H, Wa = W;
-  if (stride == 2) {
-    const size_t need = (size_t)N * H * W * C * 2;
-    B200_REQUIRE(ws && ws_bytes >= need, "conv2d_fprop: workspace too small (%zu < %zu)", ws_bytes,
-                 need);
-    launch_k(parity_kernel<false>, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)x, (bf16*)ws, N, H, W, C);
-    B200_LAUNCH_CHECK("parity_kernel<split>");
-    act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
-  }
-  TapTable tt = fprop_taps(N, C, R, S, stride, pad);
-  return run_conv_tc(act, Nact, Ha, Wa, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, stats,
-                     stats_fused, fin);
+  // stride 2: ONE launch, the taps read every other pixel of x through the TMA map's elementStrides (round 1
+  // made a parity-split copy of x first: 549 TFLOP/s against cuDNN's 724 on the 160->320 layer)
+  TapTable tt = fprop_taps(C, R, S, pad);
+  return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, stats,
+                     stats_fused, fin, stride);
 }
 
 extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
@@ -952,8 +942,8 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
 // Shifted-window wgrad launch. act: [Nact][Ha][Wa][C] bf16, dy: [N][P][Q][K] bf16,
 // dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
-                        int Q, int K, const TapTable& taps, float* dw, cudaStream_t st) {
-  if (wgrad_use_halo() && Nact == N && Ha == P && Wa == Q) {
+                        int Q, int K, const TapTable& taps, float* dw, cudaStream_t st, int cstride = 1) {
+  if (wgrad_use_halo() && Nact == N && Ha == P && Wa == Q && cstride == 1) {
     const int rc = run_wgrad_tc2h(act, dy, N, P, Q, C, K, taps, dw, st);
     if (rc >= 0) return rc;
   }
@@ -1001,9 +991,12 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   a.splits = pick_wgrad_splits(cols, a.num_ptiles, 8);
   a.taps = taps;
   a.dw = dw;
+  a.cstride = cstride;
+  B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
+               "wgrad_tc: strided TMA box exceeds 256 elements");
   if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
   CUtensorMap tmX, tmDy;
-  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn)) return rc;
+  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn, cstride)) return rc;
   if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
   if (SL == 64) return launch_wgrad_tc_cs<64>(cs, mt, tmX, tmDy, a, st);
   if (SL == 32) return launch_wgrad_tc_cs<32>(cs, mt, tmX, tmDy, a, st);
@@ -1057,18 +1050,8 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     B200_LAUNCH_CHECK("conv_wgrad_direct_kernel");
     return 0;
   }
-  const void* act = x;
-  int Nact = N, Ha = H, Wa = W;
-  if (stride == 2) {
-    const size_t need = (size_t)N * H * W * C * 2;
-    B200_REQUIRE(ws && ws_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)", ws_bytes,
-                 need);
-    launch_k(parity_kernel<false>, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)x, (bf16*)ws, N, H, W, C);
-    B200_LAUNCH_CHECK("parity_kernel<split>");
-    act = ws; Nact = 4 * N; Ha = H / 2; Wa = W / 2;
-  }
-  TapTable tt = fprop_taps(N, C, R, S, stride, pad);
-  return run_wgrad_tc(act, Nact, Ha, Wa, C, dy, N, P, Q, K, tt, dw_krsc, st);
+  TapTable tt = fprop_taps(C, R, S, pad);   // stride 2: strided TMA windows of x, no parity-split copy
+  return run_wgrad_tc(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, st, stride);
 }
 
 // -------------------------------------------------------------------------------------------------

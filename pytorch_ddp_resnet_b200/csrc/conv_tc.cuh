@@ -54,6 +54,8 @@ struct ConvTcArgs {
   int probe_rowoff;                 // PROBE ONLY: A box loaded `rowoff` pixels early, descriptor starts rowoff rows in
   int probe_baseoff;                // PROBE ONLY: value of the descriptor's base_offset field
   int gblk;                         // K-blocks per pipeline stage (SM-pair kernel)
+  int cstride;                      // conv stride: window origin = output pixel * cstride + tap displacement
+                                    // (stride 2 reads every other pixel through the TMA map's elementStrides)
   uint32_t block_bytes;             // shared-memory bytes of one K-block (A tile + B tile)
   TapTable taps;
   bf16* out;
@@ -201,8 +203,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const int nt = ct % args.n_ntiles;
       const int mt = (ct / args.n_ntiles) * CS + crank;
-      const int w0 = (mt % args.tiles_w) * args.bw;
-      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
+      const int w0 = (mt % args.tiles_w) * args.bw * args.cstride;
+      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh * args.cstride;
       const int n0 = (mt / tiles_hw) * args.bn;
       for (int t = 0; t < args.taps.n; ++t) {
         const int cw = w0 + args.taps.dw[t];
@@ -407,8 +409,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
       const int mt = (ct / args.n_ntiles) * 2 + crank;
-      const int w0 = (mt % args.tiles_w) * args.bw;
-      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh;
+      const int w0 = (mt % args.tiles_w) * args.bw * args.cstride;
+      const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh * args.cstride;
       const int n0 = (mt / tiles_hw) * args.bn;
       for (int st = 0; st < nst; ++st) {
         const int blk0 = st * args.gblk;
@@ -857,6 +859,7 @@ struct WgradTcArgs {
   int ktot;              // ntaps * Cin: row pitch of dw
   int stages;
   int tmem_cols;
+  int cstride;           // conv stride: x window origin = dY pixel * cstride + tap displacement
   uint32_t stage_bytes;
   uint32_t slab_bytes;   // rows per stage * SL * 2 (also the descriptor's leading byte offset)
   TapTable taps;
@@ -971,7 +974,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int i = 0; i < Cfg::SLABS_PER_MTILE; ++i) {
             if (i < na[j])
               tma_load_4d(a_dst + (size_t)j * a_tile_bytes + (size_t)i * args.slab_bytes, &tmX,
-                          &full_bar[s], sc[j][i], w0 + sw[j][i], h0 + sh[j][i], n0 + sn[j][i]);
+                          &full_bar[s], sc[j][i], w0 * args.cstride + sw[j][i], h0 * args.cstride + sh[j][i],
+                          n0 + sn[j][i]);
           }
         }
         if (CS == 1) {
