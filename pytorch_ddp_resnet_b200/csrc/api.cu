@@ -492,13 +492,22 @@ static int launch_conv_tc_cs(int cs, const CUtensorMap& tmA, const CUtensorMap& 
   }
 }
 
+// Output phases of a stride-2 dgrad run as ONE launch of the SM-pair kernel (see ConvTcArgs::nphase).
+struct PhasePlan {
+  int nphase;
+  int tap0[5];
+  int id[4];
+};
+
 // One shifted-window GEMM launch. act: [Nact][Ha][Wa][Cin] (bf16), wmat: [Cout][ntaps*Cin] (bf16),
 // out: [Nimg][P][Q][Cout].
 static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                        int wcols, const TapTable& taps, void* out, const void* residual,
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
                        double* stats = nullptr, bool* stats_fused = nullptr,
-                       const EpiStatsFinal* finp = nullptr, int cstride = 1) {
+                       const EpiStatsFinal* finp = nullptr, int cstride = 1,
+                       const PhasePlan* phases = nullptr) {
+  // phases != nullptr: (P, Q) is the FULL output extent, tiles are planned on the (P/2, Q/2) phase grid
   EpiStatsFinal fin;
   memset(&fin, 0, sizeof(fin));
   if (finp) fin = *finp;
@@ -508,18 +517,27 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   int KC = pick_kc(Cin);
   const int BN = pick_bn(Cout, 16, 256);
   B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
-  TilePlan t = plan_tiles(Nimg, P, Q);
+  TilePlan t = phases ? plan_tiles(Nimg, P / 2, Q / 2) : plan_tiles(Nimg, P, Q);
   ConvTcArgs a;
   memset(&a, 0, sizeof(a));
   a.bw = t.bw; a.bh = t.bh; a.bn = t.bn; a.rows_valid = t.rows_valid;
   a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
   const int m_tiles_all = t.tiles_w * t.tiles_h * t.tiles_n;
   const bool pair = conv_use_pair() && m_tiles_all % 2 == 0 && BN % 32 == 0;
+  B200_REQUIRE(!phases || pair, "conv_tc: the phased launch needs the SM-pair kernel");
+  a.nphase = 1;
+  a.phase_tap0[0] = 0;
+  a.phase_tap0[1] = taps.n;
+  if (phases) {
+    a.nphase = phases->nphase;
+    for (int i = 0; i < 5; ++i) a.phase_tap0[i] = phases->tap0[i];
+    for (int i = 0; i < 4; ++i) a.phase_id[i] = phases->id[i];
+  }
   // (tried: 64-channel blocks with a partial last block per tap for Cin = 160 - the extra predicate per
   //  MMA slowed the issue loop more than SWIZZLE_128B gained; KC stays a divisor of Cin)
   // halo-reuse kernel: 3x3 taps with unit displacements on an un-split input, maps that tile in 8x16
   {
-    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg && cstride == 1;
+    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg && cstride == 1 && !phases;
     for (int i = 0; unit && i < taps.n; ++i)
       unit = taps.dn[i] == 0 && taps.dh[i] >= -1 && taps.dh[i] <= 1 && taps.dw[i] >= -1 && taps.dw[i] <= 1;
     const int mt8x16 = (Q / 8) * (P / 16) * Nimg;
@@ -547,7 +565,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   }
   a.BN = BN; a.n_ntiles = Cout / BN; a.nkc = (Cin + KC - 1) / KC; a.cin = Cin;
   a.P = P; a.Q = Q; a.Nimg = Nimg; a.ldo = Cout;
-  a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles;
+  a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles * a.nphase;
   a.taps = taps;
   a.cstride = cstride;
   B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
@@ -744,7 +762,51 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
       }
     return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dx, addend, nullptr, N, H, W, st);
   }
-  // stride 2: one launch per output parity phase (a, b), into the parity-split workspace
+  // stride 2, ONE launch: the four output parity phases (a, b) are extra tiles of the SM-pair kernel, each
+  // with its own subset of the taps; the epilogue writes dx (+ addend) in place at (2h' + a, 2w' + b).
+  // (round 1: one launch per phase into a phase-split workspace + a merge kernel: 409 / 512 TFLOP/s)
+  {
+    PhasePlan pp;
+    memset(&pp, 0, sizeof(pp));
+    TapTable all;
+    memset(&all, 0, sizeof(all));
+    int cnt[4];
+    for (int ph = 0; ph < 4; ++ph) {
+      cnt[ph] = 0;
+      for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s)
+          if (mod2((ph >> 1) + pad - r) == 0 && mod2((ph & 1) + pad - s) == 0) ++cnt[ph];
+    }
+    int order[4] = {0, 1, 2, 3};
+    std::stable_sort(order, order + 4, [&](int x, int y) { return cnt[x] > cnt[y]; });   // heaviest first
+    const bool all_phases = cnt[0] > 0 && cnt[1] > 0 && cnt[2] > 0 && cnt[3] > 0;
+    const int BNd = pick_bn(C, 16, 256);
+    const TilePlan tp = plan_tiles(N, H / 2, W / 2);
+    const bool pair_ok = conv_use_pair() && BNd > 0 && BNd % 32 == 0 &&
+                         (tp.tiles_w * tp.tiles_h * tp.tiles_n) % 2 == 0 && R * S <= TC_MAX_TAPS;
+    static const int single = env_int("B200_DGRAD_S2_SINGLE", 1);
+    if (all_phases && pair_ok && single) {
+      pp.nphase = 4;
+      for (int i = 0; i < 4; ++i) {
+        const int ph = order[i], pa = ph >> 1, pb = ph & 1;
+        pp.id[i] = ph;
+        pp.tap0[i] = all.n;
+        for (int r = 0; r < R; ++r) {
+          if (mod2(pa + pad - r) != 0) continue;
+          for (int s = 0; s < S; ++s) {
+            if (mod2(pb + pad - s) != 0) continue;
+            const int t = all.n++;
+            all.dh[t] = floordiv2(pa + pad - r); all.dw[t] = floordiv2(pb + pad - s); all.dn[t] = 0;
+            all.wcol[t] = (r * S + s) * K;
+          }
+        }
+      }
+      pp.tap0[4] = all.n;
+      return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, all, dx, addend, nullptr, N, H, W, st, nullptr,
+                         nullptr, nullptr, 1, &pp);
+    }
+  }
+  // fallback: one launch per output parity phase (a, b), into the parity-split workspace
   const size_t need = (size_t)N * H * W * C * 2;
   B200_REQUIRE(ws && ws_bytes >= need, "conv2d_dgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   const int H2 = H / 2, W2 = W / 2;

@@ -56,6 +56,14 @@ struct ConvTcArgs {
   int gblk;                         // K-blocks per pipeline stage (SM-pair kernel)
   int cstride;                      // conv stride: window origin = output pixel * cstride + tap displacement
                                     // (stride 2 reads every other pixel through the TMA map's elementStrides)
+  // Output phases (SM-pair kernel; stride-2 dgrad in ONE launch): with nphase = 4 a unit is (phase, pixel tile,
+  // channel tile); phase ph = 2a + b covers the output pixels (2h' + a, 2w' + b), tiles are boxes in (w', h', n),
+  // and only the taps [phase_tap0[ph], phase_tap0[ph+1]) of the table contribute to it. Units are ordered
+  // phase-major, heaviest phase first, so the round-robin schedule hands every SM pair a similar mix.
+  // nphase = 1: one phase holding all taps (phase_tap0 = {0, taps.n}).
+  int nphase;
+  int phase_tap0[5];
+  int phase_id[4];                  // ph -> 2a + b (the phases are sorted by tap count)
   uint32_t block_bytes;             // shared-memory bytes of one K-block (A tile + B tile)
   TapTable taps;
   bf16* out;
@@ -399,16 +407,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_ptiles = args.num_tiles >> 1;  // pair tiles
   const int bhalf = args.BN >> 1;
 
-  const int nk = args.taps.n * args.nkc;                    // K-blocks per tile
-  const int nst = (nk + args.gblk - 1) / args.gblk;         // pipeline stages per tile
+  const int units_per_phase = num_ptiles / args.nphase;
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     // a stage holds up to gblk K-blocks (any mix of taps / channel chunks), one barrier round trip
     int s = 0;
     uint32_t ph = 0;
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
-      const int nt = ct % args.n_ntiles;
-      const int mt = (ct / args.n_ntiles) * 2 + crank;
+      const int phs = ct / units_per_phase;
+      const int cu = ct - phs * units_per_phase;
+      const int tap0 = args.phase_tap0[phs];
+      const int nk = (args.phase_tap0[phs + 1] - tap0) * args.nkc;   // K-blocks of this unit
+      const int nst = (nk + args.gblk - 1) / args.gblk;              // pipeline stages of this unit
+      const int nt = cu % args.n_ntiles;
+      const int mt = (cu / args.n_ntiles) * 2 + crank;
       const int w0 = (mt % args.tiles_w) * args.bw * args.cstride;
       const int h0 = ((mt / args.tiles_w) % args.tiles_h) * args.bh * args.cstride;
       const int n0 = (mt / tiles_hw) * args.bn;
@@ -422,8 +434,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (leader) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)cnt * args.tx_bytes);
           for (int g = 0; g < cnt; ++g) {
             const int blk = blk0 + g;
-            const int t = blk / args.nkc;
-            const int kc = blk - t * args.nkc;
+            const int tl = blk / args.nkc;
+            const int kc = blk - tl * args.nkc;
+            const int t = tap0 + tl;
             uint8_t* a_dst = base + (size_t)g * args.block_bytes;
             tma_load_4d_2sm(a_dst, &tmA, full_leader, kc * KC, w0 + args.taps.dw[t],
                             h0 + args.taps.dh[t], n0 + args.taps.dn[t]);
@@ -447,6 +460,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int as = 0;
       uint32_t aph = 0;
       for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+        const int phs = ct / units_per_phase;
+        const int nk = (args.phase_tap0[phs + 1] - args.phase_tap0[phs]) * args.nkc;
+        const int nst = (nk + args.gblk - 1) / args.gblk;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
@@ -496,11 +512,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       epi_bar();
     }
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
-      const int nt = ct % args.n_ntiles;
-      const int mt = (ct / args.n_ntiles) * 2 + crank;
-      const int w = (mt % args.tiles_w) * args.bw + wi;
-      const int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
+      const int phs = ct / units_per_phase;
+      const int cu = ct - phs * units_per_phase;
+      const int nt = cu % args.n_ntiles;
+      const int mt = (cu / args.n_ntiles) * 2 + crank;
+      int w = (mt % args.tiles_w) * args.bw + wi;
+      int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
       const int n = (mt / tiles_hw) * args.bn + ni;
+      if (args.nphase > 1) {   // output pixel (2h' + a, 2w' + b) of phase 2a + b; P, Q are the full extents
+        const int pid = args.phase_id[phs];
+        h = 2 * h + (pid >> 1);
+        w = 2 * w + (pid & 1);
+      }
       const bool valid = (m < args.rows_valid) && (w < args.Q) && (h < args.P) && (n < args.Nimg);
       const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
       const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
