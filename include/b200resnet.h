@@ -198,6 +198,21 @@ int b200_linear_bwd(const void* dlogits, const void* x, const float* w, void* dx
 int b200_ce_topk(const void* logits, const int64_t* labels, float* out, void* dlogits,
                  const float* grad_scale, int B, int O, b200_stream_t stream);
 
+/* ---- input pipeline (the step BEFORE the hot path: resnet/utils/transform_util.py:32-205 applied per sample
+ * by the DataLoader, data_util.py:218-227, then x.to(device), training.py:94) --------------------------------
+ * One launch builds a whole batch from a device-resident uint8 dataset data[M][H][W][C]:
+ *   out[b] = crop( pad( flip( whiten( to_tensor( data[index[b]] ) ) ) ) )
+ * to_tensor: x/255 (ToTensorTransform); whiten: (x - mean) / stddev with per-pixel-and-channel statistics
+ * [C][H][W] (mean NULL: none; stddev NULL: zero-mean only); flip[b] != 0: horizontal flip (NULL: none);
+ * pad / pad_mirror: PaddingTransform zero or 'reflect'; top[b], left[b]: RandomCropTransform offsets into the
+ * padded image (NULL: no crop, the output is the whole padded image). The random draws are inputs.
+ * Outputs (either may be NULL): fp32 [B][C][out_h][out_w] — bit-identical to the reference pipeline — and
+ * bf16 [B][out_h][out_w][C], the NHWC tensor the stem convolution consumes. */
+int b200_augment_batch(const void* data, const int64_t* index, const void* flip, const int32_t* top,
+                       const int32_t* left, const float* mean, const float* stddev, int B, int H, int W,
+                       int C, int pad, int pad_mirror, int out_h, int out_w, int to_tensor,
+                       float* out_f32_nchw, void* out_bf16_nhwc, b200_stream_t stream);
+
 /* ---- optimizer (torch.optim.SGD via optim_util.py:11-18, stepped at training.py:108-113) ------
  * One launch for `n` tensors. Per element: g = grad (* inv_scale); g += wd * p;
  * buf = first_step ? g : momentum*buf + (1-dampening)*g; g = nesterov ? g + momentum*buf : buf;

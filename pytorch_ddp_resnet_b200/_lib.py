@@ -56,6 +56,7 @@ SIGNATURES = {
     "b200_sgd_step": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float,
                               c_int, c_int, _P, _P, _P, _P]),
     "b200_tick": (c_int, [_P, _P]),
+    "b200_augment_batch": (c_int, [_P] * 7 + [c_int] * 9 + [_P, _P, _P]),
 }
 
 _lib = None

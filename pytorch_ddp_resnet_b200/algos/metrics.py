@@ -67,3 +67,47 @@ def global_means(metrics, world_size):
         tc.distributed.all_reduce(packed, op=tc.distributed.ReduceOp.SUM)
     vals = (packed / world_size).tolist()
     return Counter(dict(zip(names, vals)))
+
+
+class LaggedMetrics:
+    """Metrics without a blocking host read in the step that produced them (reference: metrics.py:32-41 does one
+    all-reduce + one `.item()` per metric per microbatch, i.e. three device syncs per step).
+    push(): packs the device scalars, all-reduces them once, starts an asynchronous copy into pinned host memory
+    and records an event - nothing waits. pop(): returns the values of the OLDEST pushed step once its event has
+    completed (by then the device is a whole step further, so the wait is nil)."""
+
+    def __init__(self, world_size: int, depth: int = 2):
+        self.world_size, self.depth = world_size, depth
+        self.slots = []      # (tag, names, pinned host tensor, event)
+        self.free = []
+
+    def push(self, tag, metrics) -> None:
+        names = list(metrics)
+        packed = tc.stack([metrics[k].detach().float().reshape(()) for k in names])
+        if self.world_size > 1 and tc.distributed.is_available() and tc.distributed.is_initialized():
+            tc.distributed.all_reduce(packed, op=tc.distributed.ReduceOp.SUM)
+        if self.free:
+            host, ev = self.free.pop()
+        else:
+            host = tc.empty(len(names), dtype=tc.float32)
+            host = host.pin_memory() if packed.is_cuda else host
+            ev = tc.cuda.Event() if packed.is_cuda else None
+        host.copy_(packed, non_blocking=True)
+        if ev is not None:
+            ev.record()
+        self.slots.append((tag, names, host, ev))
+
+    def ready(self) -> bool:
+        return len(self.slots) >= self.depth
+
+    def pop(self):
+        """(tag, Counter of global means) of the oldest pushed step."""
+        tag, names, host, ev = self.slots.pop(0)
+        if ev is not None:
+            ev.synchronize()
+        vals = (host / self.world_size).tolist()
+        self.free.append((host, ev))
+        return tag, Counter(dict(zip(names, vals)))
+
+    def __len__(self):
+        return len(self.slots)

@@ -7,6 +7,11 @@ triggers, evaluation after every epoch.
 What differs is below the API: the model computes in bf16 on the sm_100a kernels on its own (no
 torch autocast context is needed; a GradScaler is still honoured if one is passed), and the three
 logged metrics travel to the host in one packed all-reduce + one read per microbatch instead of three.
+With `lagged_metrics: True` (config key; implied by `cuda_graph: True`) that read does not block either:
+the metrics of step i are copied to pinned host memory asynchronously and printed / written to TensorBoard
+while step i+1 runs (the reference syncs the device three times per step, metrics.py:32-41). Anything that
+needs the loss of the CURRENT step on the host - a ReduceLROnPlateau stepped per batch, a
+PerformanceCheckpointStrategy per batch - switches the lag off.
 """
 from collections import Counter
 from typing import Any, Dict, Optional, Union
@@ -14,8 +19,8 @@ from typing import Any, Dict, Optional, Union
 import torch as tc
 
 from pytorch_ddp_resnet_b200.algos.evaluation import evaluation_loop
-from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics, global_means
-from pytorch_ddp_resnet_b200.utils.checkpoint_util import save_checkpoints
+from pytorch_ddp_resnet_b200.algos.metrics import LaggedMetrics, compute_losses_and_metrics, global_means
+from pytorch_ddp_resnet_b200.utils.checkpoint_util import FrequencyCheckpointStrategy, save_checkpoints
 
 
 def requires_loss(scheduler) -> bool:
@@ -73,6 +78,22 @@ def training_loop(
         'scaler': scaler
     }
     epoch = int(checkpoint_strategy.epoch_step)
+    # metrics read one step late (no host sync in the step): only when nothing consumes the current loss
+    loss_needed_now = (scheduler is not None and scheduler_step_unit == 'batch' and requires_loss(scheduler)) or \
+        (checkpoint_strategy.unit == 'batch' and not isinstance(checkpoint_strategy, FrequencyCheckpointStrategy))
+    lagged = bool(kwargs.get("lagged_metrics", use_graph)) and num_microbatches == 1 and not loss_needed_now
+    lag = LaggedMetrics(world_size) if lagged else None
+
+    def report(step: int, logged) -> None:
+        if rank == 0:
+            print(f"global step: {step}... loss: {logged.get('loss')}")
+            if writer:
+                for name, value in logged.items():
+                    writer.add_scalar(tag=f"train/{name}", scalar_value=value, global_step=step)
+
+    def drain(everything: bool) -> None:
+        while lag is not None and len(lag) and (everything or lag.ready()):
+            report(*lag.pop())
 
     while global_step < max_steps:
         if hasattr(sampler_train, "set_epoch"):
@@ -85,12 +106,19 @@ def training_loop(
                 if graphed is None:
                     from pytorch_ddp_resnet_b200.utils.graph_util import GraphedTrainStep
                     graphed = GraphedTrainStep(classifier, optimizer, x, y)
-                acc += global_means(graphed(x, y), world_size)
+                metrics = graphed(x, y)
+                if lagged:
+                    lag.push(global_step, metrics)
+                else:
+                    acc += global_means(metrics, world_size)
             else:
                 metrics = compute_losses_and_metrics(logits=classifier(x), labels=y)
                 loss = metrics['loss']
                 (scaler.scale(loss) if scaler else loss).backward()
-                acc += global_means(metrics, world_size)
+                if lagged:
+                    lag.push(global_step, metrics)
+                else:
+                    acc += global_means(metrics, world_size)
 
                 if microbatch_id % num_microbatches != 0:
                     continue
@@ -101,22 +129,23 @@ def training_loop(
                     optimizer.step()
                 optimizer.zero_grad(set_to_none=True)
 
-            logged = {k: v / num_microbatches for k, v in acc.items()}
-            global_loss = logged.get('loss')
+            global_loss = None
+            if lagged:
+                drain(everything=False)     # prints step i-1 while step i runs on the device
+            else:
+                logged = {k: v / num_microbatches for k, v in acc.items()}
+                global_loss = logged.get('loss')
+                report(global_step, logged)
             if scheduler and scheduler_step_unit == 'batch':
                 step_scheduler(scheduler, global_loss)
-            if rank == 0:
-                print(f"global step: {global_step}... loss: {global_loss}")
-                if writer:
-                    for name, value in logged.items():
-                        writer.add_scalar(tag=f"train/{name}", scalar_value=value, global_step=global_step)
-                if checkpoint_strategy.observe(unit='batch', loss=global_loss):
-                    save_checkpoints(checkpoint_dir=checkpoint_dir, checkpointables=checkpointables,
-                                     steps=global_step + 1)
+            if rank == 0 and checkpoint_strategy.observe(unit='batch', loss=global_loss):
+                save_checkpoints(checkpoint_dir=checkpoint_dir, checkpointables=checkpointables,
+                                 steps=global_step + 1)
             acc = Counter()
             global_step += 1
             if global_step >= max_steps:
                 break
+        drain(everything=True)
 
         val = evaluation_loop(world_size, device, dl_test, classifier)
         val_loss = val.get('loss')

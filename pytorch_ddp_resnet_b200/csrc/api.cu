@@ -16,6 +16,7 @@
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "head_sgd.cuh"
+#include "input_pipeline.cuh"
 
 using namespace b200;
 
@@ -1434,6 +1435,35 @@ extern "C" int b200_ce_topk(const void* logits, const int64_t* labels, float* ou
   const size_t threads = (size_t)B * 32;
   launch_k(ce_topk_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
   B200_LAUNCH_CHECK("ce_topk_kernel");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// input pipeline
+// -------------------------------------------------------------------------------------------------
+extern "C" int b200_augment_batch(const void* data, const int64_t* index, const void* flip, const int32_t* top,
+                                  const int32_t* left, const float* mean, const float* stddev, int B, int H,
+                                  int W, int C, int pad, int pad_mirror, int out_h, int out_w, int to_tensor,
+                                  float* out_f32_nchw, void* out_bf16_nhwc, b200_stream_t stream) {
+  B200_REQUIRE(data && index && (out_f32_nchw || out_bf16_nhwc), "augment_batch: null pointer");
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && pad >= 0, "augment_batch: bad shape");
+  B200_REQUIRE(!pad_mirror || (pad < H && pad < W), "augment_batch: mirror padding needs pad < H, W");
+  B200_REQUIRE(out_h > 0 && out_w > 0 && out_h <= H + 2 * pad && out_w <= W + 2 * pad,
+               "augment_batch: output %dx%d does not fit the padded %dx%d image", out_h, out_w, H + 2 * pad,
+               W + 2 * pad);
+  B200_REQUIRE(!stddev || mean, "augment_batch: stddev without mean");
+  B200_REQUIRE((top == nullptr) == (left == nullptr), "augment_batch: top and left go together");
+  B200_REQUIRE(top || (out_h == H + 2 * pad && out_w == W + 2 * pad),
+               "augment_batch: a smaller output needs crop offsets");
+  AugmentArgs a;
+  a.data = reinterpret_cast<const uint8_t*>(data); a.index = index;
+  a.flip = reinterpret_cast<const uint8_t*>(flip); a.top = top; a.left = left;
+  a.mean = mean; a.stddev = stddev;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.pad = pad; a.mirror = pad_mirror; a.OH = out_h; a.OW = out_w;
+  a.to_tensor = to_tensor;
+  a.out_f32 = out_f32_nchw; a.out_bf16 = reinterpret_cast<bf16*>(out_bf16_nhwc);
+  launch_k(augment_batch_kernel, ew_grid((size_t)B * out_h * out_w), EW_THREADS, 0, as_stream(stream), a);
+  B200_LAUNCH_CHECK("augment_batch_kernel");
   return 0;
 }
 

@@ -486,3 +486,33 @@ def sgd_step(ptr_table: torch.Tensor, n: int, max_size: int, lr, momentum, dampe
     _lib.call("b200_sgd_step", base, base + row, base + 2 * row, base + 3 * row, n, max_size, float(lr),
               float(momentum), float(dampening), float(weight_decay), int(bool(nesterov)),
               int(bool(first_step)), _p(inv_scale), _p(found_inf), _p(lr_dev), _stream())
+
+
+# --------------------------------------------------------------------------------------------------
+# input pipeline
+# --------------------------------------------------------------------------------------------------
+def augment_batch(data_u8, index, *, flip=None, top=None, left=None, mean=None, stddev=None, pad: int = 0,
+                  pad_mirror: bool = False, out_hw=None, to_tensor: bool = True, want_f32: bool = False,
+                  want_bf16: bool = True):
+    """One launch: out[b] = crop(pad(flip(whiten(to_tensor(data_u8[index[b]]))))) (b200_augment_batch).
+    data_u8: uint8 [M,H,W,C] on the device; index int64 [B]; flip uint8 [B]; top/left int32 [B]; mean/stddev
+    fp32 [C,H,W]. Returns (fp32 [B,C,OH,OW] or None, bf16 [B,OH,OW,C] or None)."""
+    if not (data_u8.is_cuda and data_u8.dtype == torch.uint8 and data_u8.is_contiguous() and data_u8.dim() == 4):
+        raise _lib.B200Error("augment_batch: expected a contiguous CUDA uint8 [M,H,W,C] dataset")
+    if data_u8.device.index != torch.cuda.current_device():
+        raise _lib.B200Error("augment_batch: the dataset lives on another device than the current one")
+    _lib.require_device(data_u8.device.index or 0)
+    M, H, W, C = data_u8.shape
+    B = index.numel()
+    assert index.dtype == torch.int64 and index.is_cuda and index.is_contiguous()
+    OH, OW = out_hw if out_hw is not None else (H + 2 * pad, W + 2 * pad)
+    for t, dt in ((flip, torch.uint8), (top, torch.int32), (left, torch.int32)):
+        assert t is None or (t.dtype == dt and t.is_cuda and t.is_contiguous() and t.numel() == B)
+    for t in (mean, stddev):
+        assert t is None or (t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.numel() == C * H * W)
+    of = torch.empty((B, C, OH, OW), dtype=torch.float32, device=data_u8.device) if want_f32 else None
+    ob = torch.empty((B, OH, OW, C), dtype=torch.bfloat16, device=data_u8.device) if want_bf16 else None
+    _lib.call("b200_augment_batch", data_u8.data_ptr(), index.data_ptr(), _p(flip), _p(top), _p(left), _p(mean),
+              _p(stddev), B, H, W, C, int(pad), int(bool(pad_mirror)), OH, OW, int(bool(to_tensor)), _p(of), _p(ob),
+              _stream())
+    return of, ob

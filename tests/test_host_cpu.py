@@ -31,7 +31,10 @@ def test_library_exports_every_header_symbol():
     # pure host-side queries are callable without a GPU
     assert lib.b200_conv2d_tc_supported(0, 128, 32, 32, 160, 160, 3, 3, 1, 1) == 1
     assert lib.b200_conv2d_tc_supported(0, 128, 32, 32, 3, 160, 3, 3, 1, 1) == 0
-    assert lib.b200_conv2d_workspace_bytes(0, 128, 32, 32, 160, 320, 3, 3, 2, 1, 0) == 128 * 32 * 32 * 160 * 2
+    # stride-2 fprop / wgrad read x through strided TMA boxes (no workspace); only the multi-launch dgrad
+    # fallback needs room for its four output phases
+    assert lib.b200_conv2d_workspace_bytes(0, 128, 32, 32, 160, 320, 3, 3, 2, 1, 0) == 0
+    assert lib.b200_conv2d_workspace_bytes(1, 128, 32, 32, 160, 320, 3, 3, 2, 1, 0) == 128 * 32 * 32 * 160 * 2
     assert lib.b200_bn_workspace_bytes(131072, 160) > 0
 
 
@@ -107,6 +110,22 @@ def test_config_and_checkpoint_roundtrip(tmp_path):
     assert torch.equal(lin2.weight, lin.weight) and strat2.batch_step == 4
     perf = C.get_checkpoint_strategy("PerformanceCheckpointStrategy", {"unit": "epoch"})
     assert [perf.observe(unit="epoch", loss=l) for l in (1.0, 2.0, 0.5)] == [True, False, True]
+
+
+def test_lagged_metrics_fifo():
+    from pytorch_ddp_resnet_b200.algos.metrics import LaggedMetrics
+    lag = LaggedMetrics(world_size=1)
+    for i in range(3):
+        lag.push(i, {"loss": torch.tensor(float(i)), "top1_err": torch.tensor(0.5)})
+        if i == 0:
+            assert not lag.ready()
+    assert lag.ready() and len(lag) == 3
+    tags = []
+    while len(lag):
+        tag, m = lag.pop()
+        tags.append(tag)
+        assert m["loss"] == float(tag) and m["top1_err"] == 0.5
+    assert tags == [0, 1, 2]
 
 
 def test_plan_buckets_layout():

@@ -13,7 +13,11 @@ pytestmark = pytest.mark.gpu
 CONFIG = {
     "backend": "nccl", "world_size": 1, "master_addr": "127.0.0.1", "master_port": "12377",
     "dataset_cls_name": "SyntheticCIFAR10", "synthetic_train_size": 512, "synthetic_test_size": 128,
-    "data_aug_train": {}, "data_aug_test": {},
+    # the shipped CIFAR augmentation spec: runs through the on-device input pipeline
+    "data_aug_train": {"ToTensorTransform": {}, "StandardizeWhiteningTransform": {}, "FlipTransform": {"p": 0.5},
+                       "PaddingTransform": {"pad_size": 4, "pad_type": "mirror"},
+                       "RandomCropTransform": {"crop_size": 32}},
+    "data_aug_test": {"ToTensorTransform": {}, "StandardizeWhiteningTransform": {}},
     "architecture_spec": "c3,16,3,1,1 n a r3 r3 r3 ap8,1,0 fc64,10", "preact": False, "use_proj": False,
     "dropout_prob": 0.0, "max_steps": 12, "batch_size": 64, "num_microbatches": 1, "cuda_graph": True,
     "optimizer_cls_name": "SGD",
@@ -43,6 +47,7 @@ def test_script_train_resume_eval(tmp_path):
     ckpts = sorted(os.listdir(run_dir / "checkpoints"))
     assert "classifier_1.pth" in ckpts and "classifier_6.pth" in ckpts and "classifier_11.pth" in ckpts
     assert "optimizer_11.pth" in ckpts and "checkpoint_strategy_11.pth" in ckpts
+    assert "standardizewhiteningtransform_1.pth" in ckpts   # fitted whitening, reference file name
     # resume: the newest aligned step is picked up and nothing is left to train
     r2 = _run(["--mode", "train"] + common, tmp_path)
     assert r2.returncode == 0, r2.stderr[-2000:]
