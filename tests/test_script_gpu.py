@@ -38,7 +38,7 @@ def _run(args, cwd):
 def test_script_train_resume_eval(tmp_path):
     run_dir = tmp_path / "models_dir" / "tiny"
     run_dir.mkdir(parents=True)
-    (run_dir / "config.yaml").write_text(yaml.safe_dump(CONFIG))
+    (run_dir / "config.yaml").write_text(yaml.safe_dump(CONFIG, sort_keys=False))
     common = ["--models_dir", str(tmp_path / "models_dir"), "--run_name", "tiny", "--data_dir", str(tmp_path)]
     r = _run(["--mode", "train"] + common, tmp_path)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
