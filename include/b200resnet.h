@@ -102,6 +102,22 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbia
                       int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
                       size_t ws_bytes, b200_stream_t stream);
 
+/* ---- fp32 / TF32 precision mode ---------------------------------------------------------------------------
+ * The reference evaluates WITHOUT autocast (evaluation.py:32-39) and trains without it when no GradScaler is
+ * passed (training.py:101-102): fp32 tensors whose convolutions cuDNN runs on TF32 tensor cores (torch's
+ * default allow_tf32 for cudnn). These entry points are that mode: fp32 NHWC activations, fp32 KRSC (fprop,
+ * wgrad) / CRSK (dgrad) filters read directly by tcgen05 kind::tf32 MMAs (fp32 accumulate), fp32 outputs, no
+ * intermediate rounding of bias / residual / addend. No workspace. Shapes the TF32 path does not cover are an
+ * error (b200_conv2d_tf32_supported tells). */
+int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, int K, int R, int S, int stride, int pad);
+int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias, const float* residual,
+                           float* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                           b200_stream_t stream);
+int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx, int N, int H,
+                           int W, int C, int K, int R, int S, int stride, int pad, b200_stream_t stream);
+int b200_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw_krsc, int N, int H, int W, int C, int K,
+                           int R, int S, int stride, int pad, b200_stream_t stream);
+
 /* fp32 NCHW image batch -> bf16 NHWC (the x.to(device) + autocast input cast of training.py:94-96). */
 int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,
                                b200_stream_t stream);

@@ -56,6 +56,10 @@ SIGNATURES = {
     "b200_sgd_step": (c_int, [_P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float,
                               c_int, c_int, _P, _P, _P, _P]),
     "b200_tick": (c_int, [_P, _P]),
+    "b200_conv2d_tf32_supported": (c_int, [c_int] + _CONV_DIMS),
+    "b200_conv2d_fprop_tf32": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [_P]),
+    "b200_conv2d_dgrad_tf32": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [_P]),
+    "b200_conv2d_wgrad_tf32": (c_int, [_P, _P, _P] + _CONV_DIMS + [_P]),
     "b200_augment_batch": (c_int, [_P] * 7 + [c_int] * 9 + [_P, _P, _P]),
 }
 

@@ -145,25 +145,34 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static CUtensorMapSwizzle swizzle_for(int inner_elems) {
-  return inner_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                           : inner_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+static CUtensorMapSwizzle swizzle_for_bytes(int inner_bytes) {
+  return inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// es = element size: 2 = bf16, 4 = fp32 (read by kind::tf32 MMAs). B200_TF32_TMA_ROUND=1 makes the TMA unit
+// write TF32-rounded values (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32) instead of raw fp32 bits, which the tensor core
+// then truncates; which of the two matches cuDNN's TF32 convolutions is measured in tests/test_tf32_gpu.py.
+static CUtensorMapDataType tmap_dtype(int es) {
+  if (es == 2) return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  static const int round = env_int("B200_TF32_TMA_ROUND", 1);
+  return round ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 }
 
 // bf16 tensor [N][H][W][C] with box (bc, bw, bh, bn)
 // `pstride` > 1: the box takes every pstride-th pixel in w and h (TMA elementStrides): a stride-2 convolution
 // reads its taps straight from the full-resolution tensor, bw x bh pixels land densely in shared memory.
 static int make_tmap_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bc,
-                          int bw, int bh, int bn, int pstride = 1) {
+                          int bw, int bh, int bn, int pstride = 1, int es = 2) {
   EncodeTiledFn fn = encode_fn();
   B200_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)(bw * pstride), (cuuint32_t)(bh * pstride), (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, (cuuint32_t)pstride, (cuuint32_t)pstride, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
-                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+  cuuint32_t estr[4] = {1, (cuuint32_t)pstride, (cuuint32_t)pstride, 1};
+  CUresult r = fn(m, tmap_dtype(es), 4, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(bc * es),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS,
                "cuTensorMapEncodeTiled(4d) failed: %d (N=%d H=%d W=%d C=%d box=%d,%d,%d,%d)", (int)r,
@@ -172,15 +181,15 @@ static int make_tmap_nhwc(CUtensorMap* m, const void* ptr, int N, int H, int W, 
 }
 
 // bf16 matrix [rows][cols] (cols contiguous) with box (bc cols, br rows)
-static int make_tmap_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int bc, int br) {
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int bc, int br, int es = 2) {
   EncodeTiledFn fn = encode_fn();
   B200_REQUIRE(fn, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
   cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)br};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
-                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, tmap_dtype(es), 2, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(bc * es),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (rows=%d cols=%d box=%d,%d)",
                (int)r, rows, cols, bc, br);
@@ -362,19 +371,20 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
 }
 
 // SM-pair (cta_group::2) launch: tmB's box holds BN/2 filter rows
-template <int KC, bool STATS>
+template <int KC, bool STATS, bool TF32 = false>
 static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                            cudaStream_t st) {
   const int max_dyn = 228352;
-  B200_CUDA(ensure_max_smem<conv_tc2_kernel<KC, STATS>>(max_dyn));
-  a.a_bytes = 128u * KC * 2u;
-  const uint32_t b_bytes = ((uint32_t)(a.BN / 2) * KC * 2u + 1023u) & ~1023u;
+  constexpr uint32_t ES = TF32 ? 4u : 2u;
+  B200_CUDA(ensure_max_smem<conv_tc2_kernel<KC, STATS, TF32>>(max_dyn));
+  a.a_bytes = 128u * KC * ES;
+  const uint32_t b_bytes = ((uint32_t)(a.BN / 2) * KC * ES + 1023u) & ~1023u;
   a.block_bytes = a.a_bytes + b_bytes;
-  a.tx_bytes = (uint32_t)a.rows_valid * KC * 2u + (uint32_t)(a.BN / 2) * KC * 2u;  // per CTA, per block
+  a.tx_bytes = (uint32_t)a.rows_valid * KC * ES + (uint32_t)(a.BN / 2) * KC * ES;  // per CTA, per block
   // K-blocks per stage: at least 8 MMAs per barrier round trip (the issue loop costs ~500 cycles per
   // iteration), as long as three stages still fit
   const int budget = max_dyn - 1024;
-  int gblk = std::max(1, 8 / (KC / 16));
+  int gblk = std::max(1, 8 / (int)(KC * ES / 32));
   if (const char* e = getenv("B200_CONV_GBLK")) gblk = std::max(1, atoi(e));
   gblk = std::min(gblk, a.taps.n * a.nkc);
   while (gblk > 1 && budget / (int)(gblk * a.block_bytes) < 3) --gblk;
@@ -398,7 +408,7 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<KC, STATS>, tmA, tmB, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<KC, STATS, TF32>, tmA, tmB, a));
   B200_LAUNCH_CHECK("conv_tc2_kernel");
   return 0;
 }
@@ -507,7 +517,8 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
                        double* stats = nullptr, bool* stats_fused = nullptr,
                        const EpiStatsFinal* finp = nullptr, int cstride = 1,
-                       const PhasePlan* phases = nullptr) {
+                       const PhasePlan* phases = nullptr, int es = 2) {
+  // es = 4: fp32 / TF32 precision mode (fp32 activations, filters, output; SM-pair kernel only)
   // phases != nullptr: (P, Q) is the FULL output extent, tiles are planned on the (P/2, Q/2) phase grid
   EpiStatsFinal fin;
   memset(&fin, 0, sizeof(fin));
@@ -516,6 +527,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   // output (fused BN statistics); *stats_fused says whether the kernel that ran did it
   if (stats_fused) *stats_fused = false;
   int KC = pick_kc(Cin);
+  if (es == 4) KC = (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : 8;   // 128 / 64 / 32-byte rows of fp32
   const int BN = pick_bn(Cout, 16, 256);
   B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
   TilePlan t = phases ? plan_tiles(Nimg, P / 2, Q / 2) : plan_tiles(Nimg, P, Q);
@@ -538,7 +550,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   //  MMA slowed the issue loop more than SWIZZLE_128B gained; KC stays a divisor of Cin)
   // halo-reuse kernel: 3x3 taps with unit displacements on an un-split input, maps that tile in 8x16
   {
-    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg && cstride == 1 && !phases;
+    bool unit = taps.n == 9 && Ha == P && Wa == Q && Nact == Nimg && cstride == 1 && !phases && es == 2;
     for (int i = 0; unit && i < taps.n; ++i)
       unit = taps.dn[i] == 0 && taps.dh[i] >= -1 && taps.dh[i] <= 1 && taps.dw[i] >= -1 && taps.dw[i] <= 1;
     const int mt8x16 = (Q / 8) * (P / 16) * Nimg;
@@ -574,6 +586,17 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
+  if (es == 4) {
+    B200_REQUIRE(pair, "conv_tc (tf32): shape needs the SM-pair kernel (even pixel-tile count, Cout %% 32 == 0)");
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn, cstride, 4)) return rc;
+    if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2, 4)) return rc;
+    switch (KC) {
+      case 32: return launch_conv_tc2<32, false, true>(tmA, tmB, a, st);
+      case 16: return launch_conv_tc2<16, false, true>(tmA, tmB, a, st);
+      default: return launch_conv_tc2<8, false, true>(tmA, tmB, a, st);
+    }
+  }
   if (pair) {
     // SM pair: every CTA stages BN/2 filter rows (whole 8-row swizzle atoms, UMMA N multiple of 16)
     CUtensorMap tmA, tmB;
@@ -735,6 +758,40 @@ __global__ void parity_merge_add_kernel(const bf16* __restrict__ src, const bf16
   }
 }
 
+// Tap table of a stride-2 dgrad grouped by output parity phase, heaviest phase first (see ConvTcArgs::nphase).
+// Returns false when some phase has no tap (such a phase is all zeros and cannot be a GEMM tile).
+static bool build_dgrad_phases(int R, int S, int K, int pad, PhasePlan* pp, TapTable* all) {
+  memset(pp, 0, sizeof(*pp));
+  memset(all, 0, sizeof(*all));
+  int cnt[4];
+  for (int ph = 0; ph < 4; ++ph) {
+    cnt[ph] = 0;
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s)
+        if (mod2((ph >> 1) + pad - r) == 0 && mod2((ph & 1) + pad - s) == 0) ++cnt[ph];
+  }
+  if (R * S > TC_MAX_TAPS || !(cnt[0] > 0 && cnt[1] > 0 && cnt[2] > 0 && cnt[3] > 0)) return false;
+  int order[4] = {0, 1, 2, 3};
+  std::stable_sort(order, order + 4, [&](int x, int y) { return cnt[x] > cnt[y]; });   // heaviest first
+  pp->nphase = 4;
+  for (int i = 0; i < 4; ++i) {
+    const int ph = order[i], pa = ph >> 1, pb = ph & 1;
+    pp->id[i] = ph;
+    pp->tap0[i] = all->n;
+    for (int r = 0; r < R; ++r) {
+      if (mod2(pa + pad - r) != 0) continue;
+      for (int s = 0; s < S; ++s) {
+        if (mod2(pb + pad - s) != 0) continue;
+        const int t = all->n++;
+        all->dh[t] = floordiv2(pa + pad - r); all->dw[t] = floordiv2(pb + pad - s); all->dn[t] = 0;
+        all->wcol[t] = (r * S + s) * K;
+      }
+    }
+  }
+  pp->tap0[4] = all->n;
+  return true;
+}
+
 extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx,
                                  int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
                                  int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
@@ -768,44 +825,16 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
   // (round 1: one launch per phase into a phase-split workspace + a merge kernel: 409 / 512 TFLOP/s)
   {
     PhasePlan pp;
-    memset(&pp, 0, sizeof(pp));
     TapTable all;
-    memset(&all, 0, sizeof(all));
-    int cnt[4];
-    for (int ph = 0; ph < 4; ++ph) {
-      cnt[ph] = 0;
-      for (int r = 0; r < R; ++r)
-        for (int s = 0; s < S; ++s)
-          if (mod2((ph >> 1) + pad - r) == 0 && mod2((ph & 1) + pad - s) == 0) ++cnt[ph];
-    }
-    int order[4] = {0, 1, 2, 3};
-    std::stable_sort(order, order + 4, [&](int x, int y) { return cnt[x] > cnt[y]; });   // heaviest first
-    const bool all_phases = cnt[0] > 0 && cnt[1] > 0 && cnt[2] > 0 && cnt[3] > 0;
+    const bool all_phases = build_dgrad_phases(R, S, K, pad, &pp, &all);
     const int BNd = pick_bn(C, 16, 256);
     const TilePlan tp = plan_tiles(N, H / 2, W / 2);
     const bool pair_ok = conv_use_pair() && BNd > 0 && BNd % 32 == 0 &&
                          (tp.tiles_w * tp.tiles_h * tp.tiles_n) % 2 == 0 && R * S <= TC_MAX_TAPS;
     static const int single = env_int("B200_DGRAD_S2_SINGLE", 1);
-    if (all_phases && pair_ok && single) {
-      pp.nphase = 4;
-      for (int i = 0; i < 4; ++i) {
-        const int ph = order[i], pa = ph >> 1, pb = ph & 1;
-        pp.id[i] = ph;
-        pp.tap0[i] = all.n;
-        for (int r = 0; r < R; ++r) {
-          if (mod2(pa + pad - r) != 0) continue;
-          for (int s = 0; s < S; ++s) {
-            if (mod2(pb + pad - s) != 0) continue;
-            const int t = all.n++;
-            all.dh[t] = floordiv2(pa + pad - r); all.dw[t] = floordiv2(pb + pad - s); all.dn[t] = 0;
-            all.wcol[t] = (r * S + s) * K;
-          }
-        }
-      }
-      pp.tap0[4] = all.n;
+    if (all_phases && pair_ok && single)
       return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, all, dx, addend, nullptr, N, H, W, st, nullptr,
                          nullptr, nullptr, 1, &pp);
-    }
   }
   // fallback: one launch per output parity phase (a, b), into the parity-split workspace
   const size_t need = (size_t)N * H * W * C * 2;
@@ -864,11 +893,11 @@ static int wgrad_mtiles_per_cta() {
   return mt;
 }
 
-template <int SL, int CS, int MT>
+template <int SL, int CS, int MT, bool TF32 = false>
 static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, WgradTcArgs& a,
                            cudaStream_t st) {
   const int max_dyn = 228352;
-  B200_CUDA(ensure_max_smem<wgrad_tc_kernel<SL, CS, MT>>(max_dyn));
+  B200_CUDA(ensure_max_smem<wgrad_tc_kernel<SL, CS, MT, TF32>>(max_dyn));
   a.stage_bytes = (uint32_t)(MT * (128 / SL) + a.nb) * a.slab_bytes;
   a.stages = std::min<int>(8, (max_dyn - 1024) / (int)a.stage_bytes);
   if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
@@ -889,7 +918,7 @@ static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, Wgra
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<SL, CS, MT>, tmX, tmDy, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<SL, CS, MT, TF32>, tmX, tmDy, a));
   B200_LAUNCH_CHECK("wgrad_tc_kernel");
   return 0;
 }
@@ -1004,6 +1033,43 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
 
 // Shifted-window wgrad launch. act: [Nact][Ha][Wa][C] bf16, dy: [N][P][Q][K] bf16,
 // dw: fp32 [K][ntaps*C] (row pitch = taps.n * C).
+// fp32 / TF32 precision mode: fp32 x and dY, 16-channel slabs (64-byte rows, the byte geometry of the bf16
+// kernel's 32-channel slabs), one M tile per CTA, N tile <= 80 so that two stages fit.
+static int run_wgrad_tc_tf32(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
+                             int Q, int K, const TapTable& taps, float* dw, cudaStream_t st, int cstride) {
+  constexpr int SL = 16;
+  B200_REQUIRE(C % SL == 0 && K % SL == 0, "wgrad_tc (tf32): C and K must be multiples of 16");
+  const int BN = pick_bn(K, SL, 80);
+  B200_REQUIRE(BN > 0, "wgrad_tc (tf32): no legal N tile for K=%d", K);
+  TilePlan t = plan_tiles_mult16(N, P, Q, 128);
+  B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc (tf32): pixel tile of %d rows is not a multiple of 16", t.rows_valid);
+  WgradTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bw = t.bw; a.bh = t.bh; a.bn = t.bn;
+  a.tiles_w = t.tiles_w; a.tiles_h = t.tiles_h; a.tiles_n = t.tiles_n;
+  a.num_ptiles = t.tiles_w * t.tiles_h * t.tiles_n;
+  a.kmmas = t.rows_valid / 8;
+  a.slab_bytes = (uint32_t)((t.rows_valid * SL * 4 + 1023) / 1024 * 1024);
+  a.cin = C;
+  a.slabs_per_tap = C / SL;
+  a.nslabs_total = taps.n * a.slabs_per_tap;
+  const int spm = 128 / SL;
+  a.n_mtiles = (a.nslabs_total + spm - 1) / spm;
+  a.n_mgroups = a.n_mtiles;
+  a.BN = BN; a.n_ntiles = K / BN;
+  a.nb = BN / SL;
+  a.ktot = taps.n * C;
+  a.splits = pick_wgrad_splits(a.n_mgroups * a.n_ntiles, a.num_ptiles, 8);
+  a.taps = taps;
+  a.dw = dw;
+  a.cstride = cstride;
+  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
+  CUtensorMap tmX, tmDy;
+  if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn, cstride, 4)) return rc;
+  if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn, 1, 4)) return rc;
+  return launch_wgrad_tc<SL, 1, 1, true>(tmX, tmDy, a, st);
+}
+
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
                         int Q, int K, const TapTable& taps, float* dw, cudaStream_t st, int cstride = 1) {
   if (wgrad_use_halo() && Nact == N && Ha == P && Wa == Q && cstride == 1) {
@@ -1115,6 +1181,79 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
   }
   TapTable tt = fprop_taps(C, R, S, pad);   // stride 2: strided TMA windows of x, no parity-split copy
   return run_wgrad_tc(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, st, stride);
+}
+
+// -------------------------------------------------------------------------------------------------
+// fp32 / TF32 precision mode (the reference's evaluation path and its non-AMP training path)
+// -------------------------------------------------------------------------------------------------
+extern "C" int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, int K, int R, int S, int stride,
+                                          int pad) {
+  int P, Q;
+  if (N < 1 || R * S > TC_MAX_TAPS || (stride != 1 && stride != 2)) return 0;
+  if (!same_geometry(H, W, R, S, stride, pad, &P, &Q)) return 0;
+  if (pass == B200_PASS_WGRAD) {
+    if (C % 16 != 0 || K % 16 != 0) return 0;
+    return plan_tiles_mult16(N, P, Q, 128).rows_valid % 16 == 0;
+  }
+  // fprop / dgrad run on the SM-pair kernel only: even pixel-tile count, N tile a multiple of 32
+  const int Cin = pass == B200_PASS_DGRAD ? K : C, Cout = pass == B200_PASS_DGRAD ? C : K;
+  if (Cin % 8 != 0) return 0;
+  const int BN = pick_bn(Cout, 16, 256);
+  if (BN <= 0 || BN % 32 != 0) return 0;
+  const int Po = pass == B200_PASS_DGRAD ? H : P, Qo = pass == B200_PASS_DGRAD ? W : Q;
+  TilePlan t = (pass == B200_PASS_DGRAD && stride == 2) ? plan_tiles(N, Po / 2, Qo / 2) : plan_tiles(N, Po, Qo);
+  if ((t.tiles_w * t.tiles_h * t.tiles_n) % 2 != 0) return 0;
+  if (pass == B200_PASS_DGRAD && stride == 2 && (R < 2 || S < 2)) return 0;
+  return 1;
+}
+
+extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias,
+                                      const float* residual, float* y, int N, int H, int W, int C, int K,
+                                      int R, int S, int stride, int pad, b200_stream_t stream) {
+  B200_REQUIRE(x && w_krsc && y, "conv2d_fprop_tf32: null pointer");
+  B200_REQUIRE(b200_conv2d_tf32_supported(B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad),
+               "conv2d_fprop_tf32: shape not supported in the fp32/TF32 mode");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  TapTable tt = fprop_taps(C, R, S, pad);
+  return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, as_stream(stream),
+                     nullptr, nullptr, nullptr, stride, nullptr, 4);
+}
+
+extern "C" int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx,
+                                      int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                                      b200_stream_t stream) {
+  B200_REQUIRE(dy && w_crsk && dx, "conv2d_dgrad_tf32: null pointer");
+  B200_REQUIRE(b200_conv2d_tf32_supported(B200_PASS_DGRAD, N, H, W, C, K, R, S, stride, pad),
+               "conv2d_dgrad_tf32: shape not supported in the fp32/TF32 mode");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = as_stream(stream);
+  if (stride == 1) {
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        const int i = tt.n++;
+        tt.dh[i] = pad - r; tt.dw[i] = pad - s; tt.dn[i] = 0;
+        tt.wcol[i] = (r * S + s) * K;
+      }
+    return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dx, addend, nullptr, N, H, W, st, nullptr,
+                       nullptr, nullptr, 1, nullptr, 4);
+  }
+  PhasePlan pp;
+  TapTable all;
+  build_dgrad_phases(R, S, K, pad, &pp, &all);
+  return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, all, dx, addend, nullptr, N, H, W, st, nullptr, nullptr,
+                     nullptr, 1, &pp, 4);
+}
+
+extern "C" int b200_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw_krsc, int N, int H, int W,
+                                      int C, int K, int R, int S, int stride, int pad, b200_stream_t stream) {
+  B200_REQUIRE(dy && x && dw_krsc, "conv2d_wgrad_tf32: null pointer");
+  B200_REQUIRE(b200_conv2d_tf32_supported(B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad),
+               "conv2d_wgrad_tf32: shape not supported in the fp32/TF32 mode");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  TapTable tt = fprop_taps(C, R, S, pad);
+  return run_wgrad_tc_tf32(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, as_stream(stream), stride);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -362,6 +362,29 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (the tensor core uses the upper 19 bits), fp32 accumulate, K = 8
+__device__ __forceinline__ void umma_tf32_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -414,17 +437,22 @@ __device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
 // 32-bit instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
 //   c_format [4,6)=1 (f32)  a_format [7,10)=1 (bf16)  b_format [10,13)=1 (bf16)
 //   a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major)  n>>3 [17,23)  m>>4 [24,29)
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
-                                                             int b_mn_major) {
+//   operand format: 0 = f16, 1 = bf16, 2 = tf32 (kind::tf32)
+__host__ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major,
+                                                        uint32_t fmt) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
+  d |= fmt << 7;
+  d |= fmt << 10;
   d |= (uint32_t)(a_mn_major & 1) << 15;
   d |= (uint32_t)(b_mn_major & 1) << 16;
   d |= (uint32_t)(N >> 3) << 17;
   d |= (uint32_t)(M >> 4) << 24;
   return d;
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
+                                                             int b_mn_major) {
+  return make_idesc(M, N, a_mn_major, b_mn_major, 1u);
 }
 
 }  // namespace b200

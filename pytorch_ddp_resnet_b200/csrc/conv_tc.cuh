@@ -144,12 +144,18 @@ __device__ __forceinline__ void epi_stats_finalize(const EpiStatsFinal& fin, dou
   }
 }
 
-template <int KC>
-struct KMajorCfg {
-  static constexpr uint32_t ROW_BYTES = KC * 2;
+// K-major operand tile: rows of KC elements of ES bytes (128 / 64 / 32-byte rows = the three swizzle modes);
+// one MMA consumes 32 bytes of every row (16 bf16 or 8 tf32).
+template <int KC, int ES>
+struct KMajorCfgE {
+  static constexpr uint32_t ROW_BYTES = KC * ES;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;
-  static constexpr uint32_t LAYOUT = (KC == 64) ? 2u : (KC == 32) ? 4u : 6u;
+  static constexpr uint32_t LAYOUT = (ROW_BYTES == 128) ? 2u : (ROW_BYTES == 64) ? 4u : 6u;
+  static constexpr int KSTEPS = ROW_BYTES / 32;
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64 || ROW_BYTES == 32, "row = one swizzle span");
 };
+template <int KC>
+using KMajorCfg = KMajorCfgE<KC, 2>;
 
 // CS = cluster size. With CS > 1 the CS CTAs of a cluster work on CS consecutive pixel tiles of the same
 // output-channel tile in lock step; each loads 1/CS of the filter tile and multicasts it to all of them
@@ -359,10 +365,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   are local in each CTA and signalled by the leader's multicast tcgen05.commit; tempty[a] lives in the
 //   leader and collects the 8 epilogue warps of the pair.
 // -------------------------------------------------------------------------------------------------
-template <int KC, bool STATS>
+// TF32 = true: the fp32 / TF32 precision mode (the reference's evaluation path and its non-AMP training path,
+// evaluation.py:32-39, training.py:101-102): fp32 activations and filters in shared memory, kind::tf32 MMAs
+// (K = 8), fp32 output, fp32 bias / residual added without intermediate rounding. KC counts fp32 elements.
+template <int KC, bool STATS, bool TF32 = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvTcArgs args) {
+  using Cfg = KMajorCfgE<KC, TF32 ? 4 : 2>;
+  static_assert(!(TF32 && STATS), "fused statistics: bf16 training path only");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC_MAX_STAGES];
   __shared__ uint64_t empty_bar[TC_MAX_STAGES];
@@ -451,8 +462,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (leader) {
       // ===================== MMA issuer (leader CTA only) =====================
-      const uint32_t idesc = make_idesc_bf16(256, args.BN, 0, 0);
-      const uint32_t dhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
+      const uint32_t idesc = make_idesc(256, args.BN, 0, 0, TF32 ? 2u : 1u);
+      const uint32_t dhi = smem_desc_hi(Cfg::SBO, Cfg::LAYOUT);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t blk_step = args.block_bytes >> 4;
       int s = 0;
@@ -477,9 +488,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t acc = st != 0 ? 1u : 0u;
             for (int g = 0; g < cnt; ++g) {
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                umma_bf16_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, dhi),
-                                 smem_desc_join(blo + 2 * k, dhi), idesc, acc);
+              for (int k = 0; k < Cfg::KSTEPS; ++k) {
+                if (TF32)
+                  umma_tf32_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, dhi),
+                                   smem_desc_join(blo + 2 * k, dhi), idesc, acc);
+                else
+                  umma_bf16_ss_2sm(d_addr, smem_desc_join(alo + 2 * k, dhi),
+                                   smem_desc_join(blo + 2 * k, dhi), idesc, acc);
                 acc = 1u;
               }
               alo += blk_step;
@@ -538,37 +553,58 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
-        float f[16];
+        if constexpr (TF32) {   // fp32 in, fp32 out: no rounding points
+          if (valid) {
+            float* of = reinterpret_cast<float*>(args.out) + off + c;
+            const float* rf = args.residual ? reinterpret_cast<const float*>(args.residual) + off + c : nullptr;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = 0.f;
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (brow) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
+            for (int q = 0; q < 4; ++q) {
+              float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              if (brow) {
+                o.x += __ldg(brow + c + 4 * q); o.y += __ldg(brow + c + 4 * q + 1);
+                o.z += __ldg(brow + c + 4 * q + 2); o.w += __ldg(brow + c + 4 * q + 3);
+              }
+              if (rf) {
+                const float4 r = *reinterpret_cast<const float4*>(rf + 4 * q);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              *reinterpret_cast<float4*>(of + 4 * q) = o;
+            }
           }
-          if (rrow) {
-            Vec8 r0, r1;
-            r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
-            r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
-            float rf[16];
-            r0.to_float(rf);
-            r1.to_float(rf + 8);
+        } else {
+          float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
-          }
-          if (STATS) {
+          for (int j = 0; j < 16; ++j) f[j] = 0.f;
+          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]);  // statistics of the values stored
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (brow) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
+            }
+            if (rrow) {
+              Vec8 r0, r1;
+              r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
+              r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
+              float rf[16];
+              r0.to_float(rf);
+              r1.to_float(rf + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+            }
+            if (STATS) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]);  // statistics of the values stored
+            }
+            Vec8 o0, o1;
+            o0.from_float(f);
+            o1.from_float(f + 8);
+            *reinterpret_cast<uint4*>(orow + c) = o0.raw;
+            *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
           }
-          Vec8 o0, o1;
-          o0.from_float(f);
-          o1.from_float(f + 8);
-          *reinterpret_cast<uint4*>(orow + c) = o0.raw;
-          *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+          if (STATS) epi_stats_chunk(f, lane, s_part, c);
         }
-        if (STATS) epi_stats_chunk(f, lane, s_part, c);
       }
       tc_fence_before();
       __syncwarp();
@@ -889,24 +925,26 @@ struct WgradTcArgs {
   float* dw;
 };
 
-template <int SL>
+template <int SL, int ES = 2>
 struct MnMajorCfg {
-  static constexpr uint32_t ROW_BYTES = SL * 2;
+  static constexpr uint32_t ROW_BYTES = SL * ES;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;              // next group of 8 pixels
   static constexpr uint32_t LBO = 128 * ROW_BYTES;            // next channel slab (128-pixel slabs)
-  static constexpr uint32_t LAYOUT = (SL == 64) ? 2u : (SL == 32) ? 4u : 6u;
+  static constexpr uint32_t LAYOUT = (ROW_BYTES == 128) ? 2u : (ROW_BYTES == 64) ? 4u : 6u;
   static constexpr int SLABS_PER_MTILE = 128 / SL;
+  static constexpr int KPIX = 32 / ES;                        // pixels reduced by one MMA: 16 bf16 / 8 tf32
 };
 
 // MT = M tiles (128 rows of (tap, channel) each) per CTA: they share every dY stage and accumulate
 // in MT TMEM accumulators, so per MMA the CTA pulls (MT*4 KB + 5 KB)/MT instead of 9 KB through L2/TMA.
 // CS = cluster size: the CS CTAs of a cluster own consecutive M-tile groups of the same (N tile, pixel
 // range); the dY slabs they all need are loaded once (slab i by CTA i % CS) and multicast.
-template <int SL, int CS, int MT>
+// TF32 = true: fp32 x and dY (kind::tf32, 8 pixels per MMA); SL then counts fp32 channels per slab.
+template <int SL, int CS, int MT, bool TF32 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                 const __grid_constant__ WgradTcArgs args) {
-  using Cfg = MnMajorCfg<SL>;
+  using Cfg = MnMajorCfg<SL, TF32 ? 4 : 2>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[TC_MAX_STAGES];
   __shared__ uint64_t empty_bar[TC_MAX_STAGES];
@@ -964,7 +1002,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // integer divisions (ncu: the MMA warp starved while the producer never waited for a free slot).
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t tx = (uint32_t)(na_total + nb) * (uint32_t)(args.kmmas * 16) * Cfg::ROW_BYTES;
+    const uint32_t tx = (uint32_t)(na_total + nb) * (uint32_t)(args.kmmas * Cfg::KPIX) * Cfg::ROW_BYTES;
     int sc[MT][Cfg::SLABS_PER_MTILE], sw[MT][Cfg::SLABS_PER_MTILE], sh[MT][Cfg::SLABS_PER_MTILE],
         sn[MT][Cfg::SLABS_PER_MTILE];
 #pragma unroll
@@ -1019,10 +1057,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, args.BN, 1, 1);
+    const uint32_t idesc = make_idesc(128, args.BN, 1, 1, TF32 ? 2u : 1u);
     const uint32_t dhi = smem_desc_hi(Cfg::SBO, Cfg::LAYOUT);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t kstep = (16u * Cfg::ROW_BYTES) >> 4;  // descriptor-address units per 16 pixels
+    const uint32_t kstep = ((uint32_t)Cfg::KPIX * Cfg::ROW_BYTES) >> 4;  // descriptor-address units per MMA
     const uint32_t tile_step = a_tile_bytes >> 4;
     int s = 0;
     uint32_t ph = 0;
@@ -1038,9 +1076,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint64_t bd = smem_desc_join(blo + k * kstep, dhi);
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
-            umma_bf16_ss(tmem_base + (uint32_t)j * 256u,
-                         smem_desc_join(alo + j * tile_step + k * kstep, dhi), bd, idesc,
-                         (acc | (uint32_t)k) != 0 ? 1u : 0u);
+            if (TF32)
+              umma_tf32_ss(tmem_base + (uint32_t)j * 256u,
+                           smem_desc_join(alo + j * tile_step + k * kstep, dhi), bd, idesc,
+                           (acc | (uint32_t)k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_base + (uint32_t)j * 256u,
+                           smem_desc_join(alo + j * tile_step + k * kstep, dhi), bd, idesc,
+                           (acc | (uint32_t)k) != 0 ? 1u : 0u);
           }
         }
         if (CS == 1) umma_commit(&empty_bar[s]);

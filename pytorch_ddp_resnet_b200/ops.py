@@ -516,3 +516,63 @@ def augment_batch(data_u8, index, *, flip=None, top=None, left=None, mean=None, 
               _p(stddev), B, H, W, C, int(pad), int(bool(pad_mirror)), OH, OW, int(bool(to_tensor)), _p(of), _p(ob),
               _stream())
     return of, ob
+
+
+# --------------------------------------------------------------------------------------------------
+# fp32 / TF32 precision mode (the reference's un-autocast path: evaluation.py:32-39, training.py:101-102)
+# --------------------------------------------------------------------------------------------------
+def _check_f32(t: torch.Tensor, name: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise _lib.B200Error(f"{name}: expected a contiguous CUDA fp32 tensor, got {t.dtype} {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.B200Error(f"{name}: tensor lives on {t.device}, not on the current CUDA device")
+    _lib.require_device(t.device.index or 0)
+
+
+def conv_tf32_supported(pass_: int, N, H, W, C, K, R, S, stride, pad) -> bool:
+    return bool(_lib.load().b200_conv2d_tf32_supported(pass_, N, H, W, C, K, R, S, stride, pad))
+
+
+def conv_fprop_tf32(x, w_krsc, stride: int, pad: int, bias=None, residual=None):
+    """fp32 NHWC x, fp32 KRSC filter -> fp32 NHWC y through tcgen05 kind::tf32 MMAs."""
+    _check_f32(x, "conv_fprop_tf32.x")
+    _check_f32(w_krsc, "conv_fprop_tf32.w")
+    N, H, W, C = x.shape
+    K, R, S, Cw = w_krsc.shape
+    assert Cw == C
+    P, Q = _out_hw(H, W, R, S, stride, pad)
+    y = torch.empty((N, P, Q, K), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        _check_f32(residual, "conv_fprop_tf32.residual")
+        assert residual.shape == y.shape
+    _lib.call("b200_conv2d_fprop_tf32", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual), y.data_ptr(),
+              N, H, W, C, K, R, S, stride, pad, _stream())
+    return y
+
+
+def conv_dgrad_tf32(dy, w_crsk, in_hw, stride: int, pad: int, addend=None):
+    _check_f32(dy, "conv_dgrad_tf32.dy")
+    _check_f32(w_crsk, "conv_dgrad_tf32.w")
+    N, P, Q, K = dy.shape
+    C, R, S, Kw = w_crsk.shape
+    assert Kw == K
+    H, W = in_hw
+    assert _out_hw(H, W, R, S, stride, pad) == (P, Q)
+    dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dy.device)
+    if addend is not None:
+        _check_f32(addend, "conv_dgrad_tf32.addend")
+        assert addend.shape == dx.shape
+    _lib.call("b200_conv2d_dgrad_tf32", dy.data_ptr(), w_crsk.data_ptr(), _p(addend), dx.data_ptr(), N, H, W, C, K,
+              R, S, stride, pad, _stream())
+    return dx
+
+
+def conv_wgrad_tf32(dy, x, R: int, S: int, stride: int, pad: int):
+    _check_f32(dy, "conv_wgrad_tf32.dy")
+    _check_f32(x, "conv_wgrad_tf32.x")
+    N, H, W, C = x.shape
+    K = dy.shape[-1]
+    dw = torch.empty((K, R, S, C), dtype=torch.float32, device=x.device)
+    _lib.call("b200_conv2d_wgrad_tf32", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, C, K, R, S, stride,
+              pad, _stream())
+    return dw
