@@ -110,13 +110,30 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbia
  * intermediate rounding of bias / residual / addend. No workspace. Shapes the TF32 path does not cover are an
  * error (b200_conv2d_tf32_supported tells). */
 int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, int K, int R, int S, int stride, int pad);
+/* fprop accepts EVERY shape: those outside the tensor path run as im2col + TF32 GEMM (few input channels: the
+ * stems; needs the workspace) or as an exact fp32 CUDA-core convolution (channel counts below 32, odd tiles). */
+size_t b200_conv2d_tf32_workspace_bytes(int N, int H, int W, int C, int K, int R, int S, int stride, int pad);
 int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias, const float* residual,
                            float* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
-                           b200_stream_t stream);
+                           void* ws, size_t ws_bytes, b200_stream_t stream);
 int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx, int N, int H,
                            int W, int C, int K, int R, int S, int stride, int pad, b200_stream_t stream);
 int b200_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw_krsc, int N, int H, int W, int C, int K,
                            int R, int S, int stride, int pad, b200_stream_t stream);
+
+/* The fp32 activation kernels around the TF32 convolutions (forward pass of the un-autocast reference:
+ * evaluation.py:32-39): same semantics as their bf16 namesakes, fp32 NHWC in and out, no intermediate rounding. */
+int b200_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int H, int W, b200_stream_t stream);
+int b200_bn_act_fwd_f32(const float* x, float* y, int N, int H, int W, int C, const float* mean,
+                        const float* stat, int stat_is_var, float eps, const float* gamma, const float* beta,
+                        const float* skip, int skip_mode, int skip_C, int relu, b200_stream_t stream);
+int b200_subsample2_f32(const float* x, float* y, int N, int H, int W, int C, b200_stream_t stream);
+int b200_pool_fwd_f32(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad,
+                      int is_max, b200_stream_t stream);
+int b200_linear_fwd_f32(const float* x, const float* w, const float* b, float* logits, int B, int I, int O,
+                        b200_stream_t stream);
+/* out (fp32[3]) = {mean cross entropy, top-1 error, top-5 error} of fp32 logits */
+int b200_ce_topk_f32(const float* logits, const int64_t* labels, float* out, int B, int O, b200_stream_t stream);
 
 /* fp32 NCHW image batch -> bf16 NHWC (the x.to(device) + autocast input cast of training.py:94-96). */
 int b200_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W,

@@ -57,7 +57,15 @@ SIGNATURES = {
                               c_int, c_int, _P, _P, _P, _P]),
     "b200_tick": (c_int, [_P, _P]),
     "b200_conv2d_tf32_supported": (c_int, [c_int] + _CONV_DIMS),
-    "b200_conv2d_fprop_tf32": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [_P]),
+    "b200_conv2d_tf32_workspace_bytes": (c_size_t, _CONV_DIMS),
+    "b200_conv2d_fprop_tf32": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [_P, c_size_t, _P]),
+    "b200_nchw_to_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_bn_act_fwd_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_float, _P, _P, _P, c_int,
+                                    c_int, c_int, _P]),
+    "b200_subsample2_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_pool_fwd_f32": (c_int, [_P, _P] + [c_int] * 8 + [_P]),
+    "b200_linear_fwd_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "b200_ce_topk_f32": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "b200_conv2d_dgrad_tf32": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [_P]),
     "b200_conv2d_wgrad_tf32": (c_int, [_P, _P, _P] + _CONV_DIMS + [_P]),
     "b200_augment_batch": (c_int, [_P] * 7 + [c_int] * 9 + [_P, _P, _P]),

@@ -1,10 +1,16 @@
 """Evaluation loop (reference: resnet/algos/evaluation.py:14-42): eval-mode forward over the test
 loader (BN from running statistics, dropout off), per-batch metric means, global mean over ranks.
-Metrics stay on the device until the single host read at the end."""
+Metrics stay on the device until the single host read at the end.
+
+Precision: the reference evaluates WITHOUT autocast (evaluation.py:32-39), i.e. fp32 tensors whose convolutions
+run on TF32 tensor cores. `eval_precision: tf32` (the default) does the same here: fp32 activations, kind::tf32
+convolutions on the fp32 master weights, fp32 BN / head / loss. `eval_precision: bf16` reuses the training
+kernels (about twice as fast, logits within bf16 rounding of the fp32 ones)."""
 from typing import Any, Dict
 
 import torch as tc
 
+from pytorch_ddp_resnet_b200 import ops
 from pytorch_ddp_resnet_b200.algos.metrics import compute_losses_and_metrics, global_means
 
 
@@ -21,9 +27,11 @@ def evaluation_loop(world_size: int, device, dl_test, classifier, **kwargs: Dict
     """
     classifier.eval()
     sums, num_batch = None, 0
+    mode = kwargs.get("eval_precision", "tf32") if tc.device(device).type == "cuda" else "bf16"
     for x, y in dl_test:
         x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
-        m = compute_losses_and_metrics(logits=classifier(x), labels=y)
+        with ops.precision(mode):
+            m = compute_losses_and_metrics(logits=classifier(x), labels=y)
         vec = tc.stack([m["loss"].float(), m["top1_err"].float(), m["top5_err"].float()])
         sums = vec if sums is None else sums + vec
         num_batch += 1

@@ -16,6 +16,11 @@ class _CeTopKFn(tc.autograd.Function):
     def forward(ctx, logits, labels):
         if not logits.is_cuda:
             raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if logits.dtype == tc.float32 and ops.get_precision() == "tf32":
+            # fp32 / TF32 evaluation: loss and top-k straight from the fp32 logits (forward only)
+            out, _ = ops.ce_topk(logits.contiguous(), labels.contiguous(), want_metrics=True)
+            ctx.mark_non_differentiable(out)
+            return out[0], out[1], out[2]
         lg = logits if (logits.dtype == tc.bfloat16 and logits.is_contiguous()) else logits.to(tc.bfloat16).contiguous()
         out, _ = ops.ce_topk(lg, labels.contiguous(), want_metrics=True)
         ctx.save_for_backward(lg, labels)

@@ -31,11 +31,33 @@ def as_nhwc(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
     v = x.permute(0, 2, 3, 1)
+    if ops.get_precision() == "tf32":
+        # fp32 / TF32 mode (the reference's un-autocast evaluation): activations stay fp32
+        if x.dtype == torch.float32 and v.is_contiguous():
+            return v
+        if x.dtype == torch.float32 and x.is_contiguous():
+            return ops.nchw_f32_to_nhwc_f32(x)
+        return v.to(torch.float32).contiguous()
     if x.dtype == torch.bfloat16 and v.is_contiguous():
         return v
     if x.dtype == torch.float32 and x.is_contiguous():
         return ops.nchw_f32_to_nhwc_bf16(x)
     return v.to(torch.bfloat16).contiguous()
+
+
+def require_forward_only(training: bool) -> None:
+    if training:
+        raise B200Error("the fp32 / TF32 precision mode is forward-only (evaluation, as the reference uses it: "
+                        "evaluation.py:32-39); call .eval() or train in the default bf16 mode")
+
+
+def conv_forward(c, a, **kw):
+    """One convolution of module `c` on activation `a` in the precision the activation carries: bf16 ->
+    the bf16 tcgen05 kernels on the cached bf16 filter copy; fp32 -> kind::tf32 on the fp32 master filter."""
+    if a.dtype == torch.float32:
+        kw.pop("want_stats", None)
+        return ops.conv_fprop_tf32(a, c.krsc().contiguous(), c.stride, c.padding, **kw)
+    return ops.conv_fprop(a, c.working_copies()[0], c.stride, c.padding, **kw)
 
 
 def as_nchw_view(x_nhwc: torch.Tensor) -> torch.Tensor:
@@ -271,6 +293,9 @@ class TopConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mod: Conv2d):
         xh = as_nhwc(x)
+        if xh.dtype == torch.float32:
+            require_forward_only(mod.training)
+            return as_nchw_view(conv_forward(mod, xh, bias=bias))
         wk, wt = mod.working_copies()
         # the stem is followed by a batch norm (first block / `n` token): sum its statistics here
         y = ops.conv_fprop(xh, wk, mod.stride, mod.padding, bias=bias, want_stats=mod.training)
@@ -304,6 +329,8 @@ class BnActFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, bn: Optional[BatchNorm2d], relu: bool):
         xh = as_nhwc(x)
         ctx.relu, ctx.affine, ctx.train = relu, bn is not None, bn is not None and bn.training
+        if xh.dtype == torch.float32:
+            require_forward_only(bn is not None and bn.training)
         if bn is None:
             y = ops.bn_act_fwd(xh, relu=relu)
             ctx.save_for_backward(y)
@@ -341,7 +368,7 @@ class PoolFn(torch.autograd.Function):
         xh = as_nhwc(x)
         y = ops.maxpool_fwd(xh, k, stride, pad) if is_max else ops.avgpool_fwd(xh, k, stride, pad)
         ctx.cfg = (k, stride, pad, is_max, tuple(xh.shape))
-        if is_max:
+        if is_max and xh.dtype != torch.float32:
             ctx.save_for_backward(xh, y)
         return as_nchw_view(y)
 
@@ -364,6 +391,9 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, mod=None):
         if not x.is_cuda:
             raise B200Error("pytorch_ddp_resnet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if x.dtype == torch.float32 and ops.get_precision() == "tf32":
+            require_forward_only(mod is not None and mod.training)
+            return ops.linear_fwd(x.contiguous(), weight, bias)   # fp32 in, fp32 weights, fp32 logits
         x2 = x if (x.dtype == torch.bfloat16 and x.is_contiguous()) else x.to(torch.bfloat16).contiguous()
         y = ops.linear_fwd(x2, weight, bias)
         ctx.mod = mod

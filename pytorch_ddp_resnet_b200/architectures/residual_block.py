@@ -21,7 +21,7 @@ from pytorch_ddp_resnet_b200 import ops, _lib
 from pytorch_ddp_resnet_b200._lib import B200Error
 from pytorch_ddp_resnet_b200.architectures.layers import (
     Conv2d, BatchNorm2d, ReLU, Dropout, AvgPool2d, as_nhwc, as_nchw_view, grad_nhwc, conv_weight_grad,
-    next_dropout_seed,
+    next_dropout_seed, conv_forward, require_forward_only,
 )
 
 
@@ -40,15 +40,18 @@ class _BlockFn(torch.autograd.Function):
         training = block.training
         preact = block._preact
         xh = as_nhwc(x)
-        wk = [c.working_copies() for c in convs]
+        f32 = xh.dtype == torch.float32     # fp32 / TF32 precision mode: forward only, fp32 master filters
+        if f32:
+            require_forward_only(training)
+        wk = [(None, None) if f32 else c.working_copies() for c in convs]
         seeds = [next_dropout_seed() if p > 0.0 else 0 for _ in range(n)]
 
         # ---- shortcut operand -----------------------------------------------------------------
         xsub = None
         if block._downsample and proj is not None:
             xsub = ops.subsample2(xh)
-            pk, pt = proj.working_copies()
-            skip, skip_mode = ops.conv_fprop(xsub, pk, 1, 0), _lib.SKIP_SAME
+            pt = None if f32 else proj.working_copies()[1]
+            skip, skip_mode = conv_forward(proj, xsub), _lib.SKIP_SAME
         elif block._downsample:
             skip, skip_mode = xh, _lib.SKIP_SUBSAMPLE_PAD
         else:
@@ -78,18 +81,17 @@ class _BlockFn(torch.autograd.Function):
                 # training: the output of these convs feeds a batch norm next (bn j+1 of this block, or
                 # the first norm after the block), so its statistics are summed in the conv epilogue
                 if j < n - 1:
-                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding, want_stats=training)
+                    h = conv_forward(c, a, want_stats=training)
                 elif skip_mode == _lib.SKIP_SAME:
-                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding, residual=skip,
-                                       want_stats=training)
+                    h = conv_forward(c, a, residual=skip, want_stats=training)
                 else:
-                    h = ops.conv_fprop(a, wk[j][0], c.stride, c.padding)
+                    h = conv_forward(c, a)
                     h = ops.bn_act_fwd(h, relu=False, skip=skip, skip_mode=skip_mode)
             out = h
         else:
             for j, c in enumerate(convs):
                 d = ops.bn_act_fwd(h, relu=False, dropout_p=p, seed=seeds[j]) if p > 0.0 else h
-                cj = ops.conv_fprop(d, wk[j][0], c.stride, c.padding, want_stats=training)
+                cj = conv_forward(c, d, want_stats=training)
                 st = bn_args(j, cj)
                 saved_act.append(d)         # conv input
                 saved_conv.append(cj)       # BN input

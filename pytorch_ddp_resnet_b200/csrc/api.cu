@@ -17,6 +17,7 @@
 #include "elementwise.cuh"
 #include "head_sgd.cuh"
 #include "input_pipeline.cuh"
+#include "f32_path.cuh"
 
 using namespace b200;
 
@@ -1192,7 +1193,10 @@ extern "C" int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, 
   if (N < 1 || R * S > TC_MAX_TAPS || (stride != 1 && stride != 2)) return 0;
   if (!same_geometry(H, W, R, S, stride, pad, &P, &Q)) return 0;
   if (pass == B200_PASS_WGRAD) {
-    if (C % 16 != 0 || K % 16 != 0) return 0;
+    // The kind::tf32 wgrad (both operands MN-major fp32) is compiled in but returned all zeros on B200 in round 2
+    // (gpurun_out/call10.out) and is switched off until that is understood: B200_TF32_WGRAD=1 enables it.
+    static const int on = env_int("B200_TF32_WGRAD", 0);
+    if (!on || C % 16 != 0 || K % 16 != 0) return 0;
     return plan_tiles_mult16(N, P, Q, 128).rows_valid % 16 == 0;
   }
   // fprop / dgrad run on the SM-pair kernel only: even pixel-tile count, N tile a multiple of 32
@@ -1207,16 +1211,58 @@ extern "C" int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, 
   return 1;
 }
 
+// im2col route of the few-input-channel stems in the fp32 mode: K = R*S*C padded to 32 fp32 columns
+static bool tf32_use_im2col(int N, int H, int W, int C, int K, int R, int S, int stride, int pad) {
+  if (C >= 8 || R * S * C > 1024) return false;
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  if (P < 1 || Q < 1) return false;
+  return b200_conv2d_tf32_supported(B200_PASS_FPROP, N, P, Q, im2col_kpad(R, S, C), K, 1, 1, 1, 0) != 0;
+}
+
+extern "C" size_t b200_conv2d_tf32_workspace_bytes(int N, int H, int W, int C, int K, int R, int S, int stride,
+                                                   int pad) {
+  if (b200_conv2d_tf32_supported(B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad)) return 0;
+  if (!tf32_use_im2col(N, H, W, C, K, R, S, stride, pad)) return 0;
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  const size_t kpad = im2col_kpad(R, S, C);
+  return align_up((size_t)N * P * Q * kpad * 4, 1024) + align_up((size_t)K * kpad * 4, 1024);
+}
+
 extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias,
                                       const float* residual, float* y, int N, int H, int W, int C, int K,
-                                      int R, int S, int stride, int pad, b200_stream_t stream) {
+                                      int R, int S, int stride, int pad, void* ws, size_t ws_bytes,
+                                      b200_stream_t stream) {
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop_tf32: null pointer");
-  B200_REQUIRE(b200_conv2d_tf32_supported(B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad),
-               "conv2d_fprop_tf32: shape not supported in the fp32/TF32 mode");
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop_tf32: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
-  TapTable tt = fprop_taps(C, R, S, pad);
-  return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, as_stream(stream),
-                     nullptr, nullptr, nullptr, stride, nullptr, 4);
+  B200_REQUIRE(P > 0 && Q > 0, "conv2d_fprop_tf32: empty output");
+  cudaStream_t st = as_stream(stream);
+  if (b200_conv2d_tf32_supported(B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad)) {
+    TapTable tt = fprop_taps(C, R, S, pad);
+    return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, nullptr, nullptr,
+                       nullptr, stride, nullptr, 4);
+  }
+  if (tf32_use_im2col(N, H, W, C, K, R, S, stride, pad)) {
+    const int kpad = im2col_kpad(R, S, C);
+    const size_t col_bytes = align_up((size_t)N * P * Q * kpad * 4, 1024);
+    B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 4, "conv2d_fprop_tf32: workspace too small");
+    float* col = reinterpret_cast<float*>(ws);
+    float* wpad = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + col_bytes);
+    launch_k(im2col_f32_kernel, ew_grid((size_t)N * P * Q * kpad), EW_THREADS, 0, st, x, col, N, H, W, C, R, S, stride, pad, P, Q, kpad);
+    B200_LAUNCH_CHECK("im2col_f32_kernel");
+    launch_k(repitch_rows_kernel<float>, ew_grid((size_t)K * kpad), EW_THREADS, 0, st, w_krsc, wpad, K, R * S * C, kpad);
+    B200_LAUNCH_CHECK("repitch_rows_kernel");
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    tt.n = 1;
+    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, nullptr, nullptr,
+                       nullptr, 1, nullptr, 4);
+  }
+  // shapes outside the TF32 tensor path (channel counts below 32, odd tile counts): exact fp32 on the CUDA cores
+  ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
+  launch_k(conv_fprop_direct_f32_kernel, ew_grid((size_t)N * P * Q * K), EW_THREADS, 0, st, x, w_krsc, bias, residual, y, d);
+  B200_LAUNCH_CHECK("conv_fprop_direct_f32_kernel");
+  return 0;
 }
 
 extern "C" int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx,
@@ -1254,6 +1300,66 @@ extern "C" int b200_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   TapTable tt = fprop_taps(C, R, S, pad);
   return run_wgrad_tc_tf32(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, as_stream(stream), stride);
+}
+
+extern "C" int b200_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int H, int W, b200_stream_t stream) {
+  B200_REQUIRE(x && y, "nchw_to_nhwc_f32: null pointer");
+  launch_k(nchw_to_nhwc_f32_kernel, ew_grid((size_t)N * C * H * W), EW_THREADS, 0, as_stream(stream), x, y, N, C, H, W);
+  B200_LAUNCH_CHECK("nchw_to_nhwc_f32_kernel");
+  return 0;
+}
+
+extern "C" int b200_bn_act_fwd_f32(const float* x, float* y, int N, int H, int W, int C, const float* mean,
+                                   const float* stat, int stat_is_var, float eps, const float* gamma,
+                                   const float* beta, const float* skip, int skip_mode, int skip_C, int relu,
+                                   b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 4 == 0, "bn_act_fwd_f32: bad arguments");
+  B200_REQUIRE(skip_mode == B200_SKIP_NONE || skip, "bn_act_fwd_f32: skip_mode set without skip tensor");
+  B200_REQUIRE(skip_mode != B200_SKIP_SUBSAMPLE_PAD || (skip_C % 4 == 0 && skip_C <= C), "bn_act_fwd_f32: bad skip_C");
+  BnActF32Args a;
+  a.x = x; a.y = y; a.skip = skip; a.mean = mean; a.stat = stat; a.gamma = gamma; a.beta = beta;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.skip_mode = skip ? skip_mode : 0; a.skip_C = skip_C;
+  a.stat_is_var = stat_is_var; a.relu = relu; a.affine = (gamma && beta && mean && stat) ? 1 : 0; a.eps = eps;
+  launch_k(bn_act_fwd_f32_kernel, ew_grid((size_t)N * H * W * C / 4), EW_THREADS, 0, as_stream(stream), a);
+  B200_LAUNCH_CHECK("bn_act_fwd_f32_kernel");
+  return 0;
+}
+
+extern "C" int b200_subsample2_f32(const float* x, float* y, int N, int H, int W, int C, b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 4 == 0, "subsample2_f32: bad arguments");
+  launch_k(subsample2_f32_kernel, ew_grid((size_t)N * H * W * C / 4), EW_THREADS, 0, as_stream(stream), x, y, N, H, W, C);
+  B200_LAUNCH_CHECK("subsample2_f32_kernel");
+  return 0;
+}
+
+extern "C" int b200_pool_fwd_f32(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad,
+                                 int is_max, b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 4 == 0 && stride >= 1, "pool_fwd_f32: bad arguments");
+  const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
+  const int grid = ew_grid((size_t)N * P * Q * C / 4);
+  if (is_max) launch_k(pool_fwd_f32_kernel<true>, grid, EW_THREADS, 0, as_stream(stream), x, y, N, H, W, C, k, stride, pad, P, Q);
+  else launch_k(pool_fwd_f32_kernel<false>, grid, EW_THREADS, 0, as_stream(stream), x, y, N, H, W, C, k, stride, pad, P, Q);
+  B200_LAUNCH_CHECK("pool_fwd_f32_kernel");
+  return 0;
+}
+
+extern "C" int b200_linear_fwd_f32(const float* x, const float* w, const float* b, float* logits, int B, int I,
+                                   int O, b200_stream_t stream) {
+  B200_REQUIRE(x && w && logits, "linear_fwd_f32: null pointer");
+  const size_t threads = (size_t)B * O * 32;
+  launch_k(linear_fwd_f32_kernel, (unsigned)((threads + 255) / 256), 256, 0, as_stream(stream), x, w, b, logits, B, I, O);
+  B200_LAUNCH_CHECK("linear_fwd_f32_kernel");
+  return 0;
+}
+
+extern "C" int b200_ce_topk_f32(const float* logits, const int64_t* labels, float* out, int B, int O,
+                                b200_stream_t stream) {
+  B200_REQUIRE(logits && labels && out, "ce_topk_f32: null pointer");
+  cudaStream_t st = as_stream(stream);
+  B200_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
+  launch_k(ce_topk_f32_kernel, (unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, st, logits, labels, out, B, O);
+  B200_LAUNCH_CHECK("ce_topk_f32_kernel");
+  return 0;
 }
 
 // -------------------------------------------------------------------------------------------------

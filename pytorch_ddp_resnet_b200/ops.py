@@ -19,6 +19,35 @@ _workspaces = {}
 _step_counters = {}
 
 
+# Precision mode of the forward pass: "bf16" (training and fast evaluation: bf16 activations, fp32 accumulate)
+# or "tf32" (the reference's un-autocast path, evaluation.py:32-39: fp32 activations, TF32 convolutions).
+# The mode only decides what a stem does with an fp32 image batch; every later kernel follows the dtype of
+# the activation it receives.
+_precision = ["bf16"]
+
+
+def get_precision() -> str:
+    return _precision[0]
+
+
+class precision:
+    """with ops.precision("tf32"): logits = model(x)   # forward-only fp32 / TF32 evaluation"""
+
+    def __init__(self, mode: str):
+        if mode not in ("bf16", "tf32"):
+            raise ValueError("precision must be 'bf16' or 'tf32'")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _precision[0]
+        _precision[0] = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        _precision[0] = self.prev
+        return False
+
+
 def step_counter(device: torch.device) -> torch.Tensor:
     """Per-device uint64 step counter (stored as int64) that the dropout kernels fold into their seed.
     It only advances through tick(): a captured training step ticks it once per replay."""
@@ -327,7 +356,22 @@ def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var:
                dropout_p: float = 0.0, seed: int = 0, running=None, want_mask: bool = False):
     """running: optional (running_mean, running_var, num_batches_tracked, momentum) updated from mean / invstd
     by the same launch (statistics that came out of a conv kernel: bn_batch_stats(...)[2] is True).
-    want_mask: also return the ReLU/dropout bit mask (uint8 [N,H,W,C/8]) for bn_act_bwd -> (y, mask)."""
+    want_mask: also return the ReLU/dropout bit mask (uint8 [N,H,W,C/8]) for bn_act_bwd -> (y, mask).
+    fp32 x: the forward-only fp32 kernel of the fp32 / TF32 mode (no dropout, no mask)."""
+    if x.dtype == torch.float32:
+        if dropout_p > 0 or want_mask or running is not None:
+            raise _lib.B200Error("bn_act_fwd: the fp32 / TF32 mode is forward-only (evaluation)")
+        _check_f32(x, "bn_act_fwd.x")
+        N, H, W, C = x.shape
+        y = torch.empty_like(x)
+        skip_C = 0
+        if skip is not None:
+            _check_f32(skip, "bn_act_fwd.skip")
+            skip_C = skip.shape[-1]
+        _lib.call("b200_bn_act_fwd_f32", x.data_ptr(), y.data_ptr(), N, H, W, C, _p(mean), _p(invstd),
+                  int(stat_is_var), eps, _p(gamma), _p(beta), _p(skip), skip_mode if skip is not None else 0, skip_C,
+                  int(relu), _stream())
+        return y
     _check_act(x, "bn_act_fwd.x")
     N, H, W, C = x.shape
     y = torch.empty_like(x)
@@ -381,9 +425,14 @@ def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = Tru
 
 
 def subsample2(x):
-    _check_act(x, "subsample2.x")
     N, H2, W2, C = x.shape
     assert H2 % 2 == 0 and W2 % 2 == 0
+    if x.dtype == torch.float32:
+        _check_f32(x, "subsample2.x")
+        y = torch.empty((N, H2 // 2, W2 // 2, C), dtype=torch.float32, device=x.device)
+        _lib.call("b200_subsample2_f32", x.data_ptr(), y.data_ptr(), N, H2 // 2, W2 // 2, C, _stream())
+        return y
+    _check_act(x, "subsample2.x")
     y = torch.empty((N, H2 // 2, W2 // 2, C), dtype=torch.bfloat16, device=x.device)
     _lib.call("b200_subsample2", x.data_ptr(), y.data_ptr(), N, H2 // 2, W2 // 2, C, _stream())
     return y
@@ -404,9 +453,15 @@ def upsample_add_(dx, g, Cg: Optional[int] = None):
 # pooling
 # --------------------------------------------------------------------------------------------------
 def _pool(name, x, k, stride, pad):
-    _check_act(x, name)
     N, H, W, C = x.shape
     P, Q = _out_hw(H, W, k, k, stride, pad)
+    if x.dtype == torch.float32:
+        _check_f32(x, name)
+        y = torch.empty((N, P, Q, C), dtype=torch.float32, device=x.device)
+        _lib.call("b200_pool_fwd_f32", x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad,
+                  int(name == "b200_maxpool_fwd"), _stream())
+        return y
+    _check_act(x, name)
     y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=x.device)
     _lib.call(name, x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, _stream())
     return y
@@ -441,9 +496,14 @@ def maxpool_bwd(dy, x, y, k, stride, pad):
 # head
 # --------------------------------------------------------------------------------------------------
 def linear_fwd(x, w, b):
-    _check_act(x, "linear_fwd.x")
     B, I = x.shape
     O = w.shape[0]
+    if x.dtype == torch.float32:
+        _check_f32(x, "linear_fwd.x")
+        y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+        _lib.call("b200_linear_fwd_f32", x.data_ptr(), w.data_ptr(), _p(b), y.data_ptr(), B, I, O, _stream())
+        return y
+    _check_act(x, "linear_fwd.x")
     y = torch.empty((B, O), dtype=torch.bfloat16, device=x.device)
     _lib.call("b200_linear_fwd", x.data_ptr(), w.data_ptr(), _p(b), y.data_ptr(), B, I, O, _stream())
     return y
@@ -463,6 +523,14 @@ def linear_bwd(dy, x, w, want_dx=True, out_dw=None, out_db=None):
 
 def ce_topk(logits, labels, want_metrics=True, want_dlogits=False, grad_scale=None):
     """(out fp32[3] = loss, top1_err, top5_err | None, dlogits bf16 | None)."""
+    if logits.dtype == torch.float32:
+        if want_dlogits:
+            raise _lib.B200Error("ce_topk: the fp32 / TF32 mode is forward-only (evaluation)")
+        _check_f32(logits, "ce_topk.logits")
+        B, O = logits.shape
+        out = torch.empty((3,), dtype=torch.float32, device=logits.device)
+        _lib.call("b200_ce_topk_f32", logits.data_ptr(), labels.data_ptr(), out.data_ptr(), B, O, _stream())
+        return out, None
     _check_act(logits, "ce_topk.logits")
     assert labels.dtype == torch.int64 and labels.is_cuda and labels.is_contiguous()
     B, O = logits.shape
@@ -545,8 +613,18 @@ def conv_fprop_tf32(x, w_krsc, stride: int, pad: int, bias=None, residual=None):
     if residual is not None:
         _check_f32(residual, "conv_fprop_tf32.residual")
         assert residual.shape == y.shape
+    nws = _lib.load().b200_conv2d_tf32_workspace_bytes(N, H, W, C, K, R, S, stride, pad)
+    ws = _workspace(x.device, nws) if nws else None
     _lib.call("b200_conv2d_fprop_tf32", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual), y.data_ptr(),
-              N, H, W, C, K, R, S, stride, pad, _stream())
+              N, H, W, C, K, R, S, stride, pad, _p(ws), nws, _stream())
+    return y
+
+
+def nchw_f32_to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
+    _check_f32(x, "nchw_f32_to_nhwc_f32.x")
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device)
+    _lib.call("b200_nchw_to_nhwc_f32", x.data_ptr(), y.data_ptr(), N, C, H, W, _stream())
     return y
 
 
