@@ -375,7 +375,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
 template <int KC, bool STATS, bool TF32 = false>
 static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                            cudaStream_t st) {
-  const int max_dyn = 228352;
+  const int max_dyn = STATS ? 228352 - 6144 : 228352;   // STATS: 8 KB of static shared memory for the partial sums
   constexpr uint32_t ES = TF32 ? 4u : 2u;
   B200_CUDA(ensure_max_smem<conv_tc2_kernel<KC, STATS, TF32>>(max_dyn));
   a.a_bytes = 128u * KC * ES;
@@ -430,7 +430,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
                             int wcols, const TapTable& taps, void* out, const void* residual,
                             const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
                             const EpiStatsFinal& fin, cudaStream_t st) {
-  const int max_dyn = 228352;
+  const int max_dyn = STATS ? 228352 - 6144 : 228352;   // STATS: 8 KB of static shared memory for the partial sums
   B200_CUDA(ensure_max_smem<conv_tc2h_kernel<KC, MT, STATS>>(max_dyn));
   ConvHaloArgs a;
   memset(&a, 0, sizeof(a));
@@ -562,9 +562,9 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       // accumulator double-buffering: the kernel is not L2->SM bound), PW=16 1168 / 1414.
       static const int mt_env = env_int("B200_HALO_MT", 1);
       static const int pw = std::max(10, std::min(16, env_int("B200_HALO_PW", 10)));
-      const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512;
+      const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512 && BN <= 8 * EPI_RES_VECS;
 #define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw
-      if (stats && !mt2 && BN <= EPI_STATS_MAX_BN) {
+      if (stats && !mt2 && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
         *stats_fused = true;
         if (KC == 64) return launch_conv_tc2h<64, 1, true>(B200_HALO_ARGS, stats, fin, st);
         return launch_conv_tc2h<32, 1, true>(B200_HALO_ARGS, stats, fin, st);
@@ -603,7 +603,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn, cstride)) return rc;
     if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
-    if (stats && BN <= EPI_STATS_MAX_BN) {
+    if (stats && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
       *stats_fused = true;
       a.stats = stats;
       a.fin = fin;
@@ -1144,7 +1144,9 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
   if (dbias) {
     B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
     B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
-    const int ppc = (int)std::max<size_t>(64, (npix + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4));
+    // ONE block per SM: every block ends with K same-address atomics, which serialise (592 blocks took 46 us
+    // for the 42 MB stem gradient in round 2's launch list, most of it in the atomics)
+    const int ppc = (int)std::max<size_t>(64, (npix + (size_t)num_sms() - 1) / (size_t)num_sms());
     launch_k(conv_dbias_kernel, dim3((unsigned)((npix + ppc - 1) / ppc), 1), 256, 0, st, (const bf16*)dy, dbias,
                                                                                     npix, K, ppc);
     B200_LAUNCH_CHECK("conv_dbias_kernel");

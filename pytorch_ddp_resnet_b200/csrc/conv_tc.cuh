@@ -82,7 +82,9 @@ struct ConvTcArgs {
 // them to the CTA's shared partials; per tile the 4 epilogue warps flush those with one fp64 atomic per
 // (channel, statistic) into slot (tile % BN_SLOTS) of the accumulator workspace (common.cuh).
 // -------------------------------------------------------------------------------------------------
+constexpr int EPI_RES_VECS = 16;          // 16-byte residual vectors prefetched per epilogue thread (128 columns)
 constexpr int EPI_STATS_MAX_BN = 256;
+constexpr int EPI_STATS_MAX_C = 1024;   // output channels a CTA can keep partial sums for (8 KB of shared memory)
 
 __device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float* s_part, int c) {
   float s[16], q[16];
@@ -112,16 +114,14 @@ __device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float
 // barrier among the 256 epilogue threads of a CTA (warps 2..9), id 1 (id 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// after the last chunk of a tile: flush the CTA's partials of output-channel tile `nt`
-__device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, int C, int BN, int nt,
-                                                int slot, int e) {
+// after the LAST tile of a CTA: flush its partial sums of all C output channels (the partials of the ~7 tiles a
+// CTA processes stay in shared memory in fp32; round 1 flushed after every tile: two more barriers and 2*BN
+// global atomics inside the tile loop)
+__device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, int C, int e) {
   epi_bar();
-  double* dst = accum + (size_t)(slot % BN_SLOTS) * bn_slot_stride(C) + (size_t)nt * BN;
-  for (int i = e; i < 2 * BN; i += TC2_EPI_THREADS) {
-    const float v = s_part[i];
-    s_part[i] = 0.f;
-    atomicAdd(dst + (size_t)(i & 1) * C + (i >> 1), (double)v);
-  }
+  double* dst = accum + (size_t)(blockIdx.x % BN_SLOTS) * bn_slot_stride(C);
+  for (int i = e; i < 2 * C; i += TC2_EPI_THREADS)
+    atomicAdd(dst + (size_t)(i & 1) * C + (i >> 1), (double)s_part[i]);
   epi_bar();
 }
 
@@ -380,7 +380,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_BN : 1];
+  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_C : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -523,7 +523,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int as = 0;
     uint32_t aph = 0;
     if (STATS) {
-      for (int i = e; i < 2 * EPI_STATS_MAX_BN; i += TC2_EPI_THREADS) s_part[i] = 0.f;
+      for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
@@ -546,10 +546,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
 
+      // residual row prefetched before the accumulator wait (see conv_tc2h_kernel)
+      Vec8 rv[EPI_RES_VECS];
+      if (!TF32 && rrow && valid) {
+#pragma unroll
+        for (int i = 0; i < EPI_RES_VECS; ++i)
+          if (c_lo + 8 * i < c_hi) rv[i].raw = ldg_stream(rrow + c_lo + 8 * i);
+      }
+
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
-      for (int c = c_lo; c < c_hi; c += 16) {
+#pragma unroll
+      for (int ci = 0; ci < EPI_RES_VECS / 2; ++ci) {
+        const int c = c_lo + 16 * ci;
+        if (c >= c_hi) break;
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -584,12 +595,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
             }
             if (rrow) {
-              Vec8 r0, r1;
-              r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
-              r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
               float rf[16];
-              r0.to_float(rf);
-              r1.to_float(rf + 8);
+              rv[2 * ci].to_float(rf);
+              rv[2 * ci + 1].to_float(rf + 8);
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
             }
@@ -603,17 +611,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             *reinterpret_cast<uint4*>(orow + c) = o0.raw;
             *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
           }
-          if (STATS) epi_stats_chunk(f, lane, s_part, c);
+          if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
-      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, e);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
-    if (STATS) epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+    if (STATS) {
+      epi_stats_flush(s_part, args.stats, args.ldo, e);
+      epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+    }
   }
 
   __syncwarp();
@@ -672,7 +682,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t bfull_bar[HALO_BSTAGES_MAX], bempty_bar[HALO_BSTAGES_MAX];
   __shared__ uint64_t tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_BN : 1];
+  __shared__ float s_part[STATS ? 2 * EPI_STATS_MAX_C : 1];
   static_assert(!STATS || MT == 1, "fused statistics: one pixel tile per CTA");
 
   const int warp = threadIdx.x >> 5;
@@ -828,7 +838,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aph = 0;
     if (STATS) {
-      for (int i = e; i < 2 * EPI_STATS_MAX_BN; i += TC2_EPI_THREADS) s_part[i] = 0.f;
+      for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
@@ -843,11 +853,24 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
 
+      // The residual row of this thread (up to 128 columns = 16 vectors) is fetched BEFORE waiting for the
+      // accumulator: ncu (profiles/r02_*) showed the epilogue of the residual variants stalled on these loads
+      // (long-scoreboard, ~18 % of all samples) when each 16-column chunk loaded its own slice after tcgen05.ld.
+      Vec8 rv[EPI_RES_VECS];
+      if (rrow) {
+#pragma unroll
+        for (int i = 0; i < EPI_RES_VECS; ++i)
+          if (c_lo + 8 * i < c_hi) rv[i].raw = ldg_stream(rrow + c_lo + 8 * i);
+      }
+
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u + (uint32_t)(t * args.BN);
-      for (int c = c_lo; c < c_hi; c += 16) {
+#pragma unroll
+      for (int ci = 0; ci < EPI_RES_VECS / 2; ++ci) {
+        const int c = c_lo + 16 * ci;
+        if (c >= c_hi) break;
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -859,12 +882,9 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
         }
         if (rrow) {
-          Vec8 r0, r1;
-          r0.raw = *reinterpret_cast<const uint4*>(rrow + c);
-          r1.raw = *reinterpret_cast<const uint4*>(rrow + c + 8);
           float rf[16];
-          r0.to_float(rf);
-          r1.to_float(rf + 8);
+          rv[2 * ci].to_float(rf);
+          rv[2 * ci + 1].to_float(rf + 8);
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
         }
@@ -877,15 +897,17 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o1.from_float(f + 8);
         *reinterpret_cast<uint4*>(orow + c) = o0.raw;
         *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
-        if (STATS) epi_stats_chunk(f, lane, s_part, c);
+        if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
-      if (STATS) epi_stats_flush(s_part, args.stats, args.ldo, args.BN, nt, ct, e);
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
-    if (STATS) epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+    if (STATS) {
+      epi_stats_flush(s_part, args.stats, args.ldo, e);
+      epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+    }
   }
 
   __syncwarp();
