@@ -58,6 +58,9 @@ def main():
         row = {"shape": [N, H, W, C, K, R, st, pad], "gflop": flops / 1e9}
         for name, fn in [
             ("fprop", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC)),
+            ("fprop_stats", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC, want_stats=True)),
+            ("fprop_res_stats", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC, want_stats=True,
+                                                         residual=dys[(i + 1) % NB])),
             ("dgrad", lambda i: ops.conv_dgrad(dys[i % NB], wt, (H, W), st, pad, algo=_lib.ALGO_TC)),
             ("wgrad", lambda i: ops.conv_wgrad(dys[i % NB], xs[i % NB], R, R, st, pad, algo=_lib.ALGO_TC)),
         ]:
