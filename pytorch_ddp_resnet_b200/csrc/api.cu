@@ -529,8 +529,14 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   if (stats_fused) *stats_fused = false;
   int KC = pick_kc(Cin);
   if (es == 4) KC = (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : 8;   // 128 / 64 / 32-byte rows of fp32
-  const int BN = pick_bn(Cout, 16, 256);
+  int BN = pick_bn(Cout, 16, 256);
   B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d", Cout);
+  // a fused residual is prefetched into registers: at most 80 columns per epilogue thread (N tile <= 160)
+  if (residual && es == 2 && BN > 16 * EPI_RES_VECS) {
+    const int bn2 = pick_bn(Cout, 32, 16 * EPI_RES_VECS);
+    BN = bn2 > 0 ? bn2 : pick_bn(Cout, 16, 16 * EPI_RES_VECS);
+    B200_REQUIRE(BN > 0, "conv_tc: no legal N tile for Cout=%d with a residual", Cout);
+  }
   TilePlan t = phases ? plan_tiles(Nimg, P / 2, Q / 2) : plan_tiles(Nimg, P, Q);
   ConvTcArgs a;
   memset(&a, 0, sizeof(a));
@@ -562,7 +568,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       // accumulator double-buffering: the kernel is not L2->SM bound), PW=16 1168 / 1414.
       static const int mt_env = env_int("B200_HALO_MT", 1);
       static const int pw = std::max(10, std::min(16, env_int("B200_HALO_PW", 10)));
-      const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512 && BN <= 8 * EPI_RES_VECS;
+      const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512 && (!residual || BN <= 8 * EPI_RES_VECS);
 #define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw
       if (stats && !mt2 && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
         *stats_fused = true;

@@ -82,7 +82,13 @@ struct ConvTcArgs {
 // them to the CTA's shared partials; per tile the 4 epilogue warps flush those with one fp64 atomic per
 // (channel, statistic) into slot (tile % BN_SLOTS) of the accumulator workspace (common.cuh).
 // -------------------------------------------------------------------------------------------------
-constexpr int EPI_RES_VECS = 16;          // 16-byte residual vectors prefetched per epilogue thread (128 columns)
+// Residual operand of the bf16 epilogues: a thread's slice of its output row (<= 80 columns = 10 16-byte
+// vectors; the host caps the N tile at 160 channels when a residual is fused) is fetched ONE TILE AHEAD into
+// registers: the loads for tile i+1 are issued when tile i's accumulator is ready and complete while tile i
+// drains. Loading inside the chunk loop, or all at once right before the drain, left the epilogue waiting a
+// full DRAM round trip per tile (86 us against 55 us for the 160-channel 32x32 layer, gpurun_out/call14).
+constexpr int EPI_RES_VECS = 10;
+constexpr int EPI_MAX_CHUNKS = 8;         // 16-column chunks per epilogue thread (N tile <= 256, two halves)
 constexpr int EPI_STATS_MAX_BN = 256;
 constexpr int EPI_STATS_MAX_C = 1024;   // output channels a CTA can keep partial sums for (8 KB of shared memory)
 
@@ -526,10 +532,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
-    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+    // output row of this thread in unit `ct`: element offset of its first column, validity, channel tile
+    auto unit_row = [&](int ct, bool& valid, int& nt) -> size_t {
       const int phs = ct / units_per_phase;
       const int cu = ct - phs * units_per_phase;
-      const int nt = cu % args.n_ntiles;
+      nt = cu % args.n_ntiles;
       const int mt = (cu / args.n_ntiles) * 2 + crank;
       int w = (mt % args.tiles_w) * args.bw + wi;
       int h = ((mt / args.tiles_w) % args.tiles_h) * args.bh + hi;
@@ -539,28 +546,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         h = 2 * h + (pid >> 1);
         w = 2 * w + (pid & 1);
       }
-      const bool valid = (m < args.rows_valid) && (w < args.Q) && (h < args.P) && (n < args.Nimg);
+      valid = (m < args.rows_valid) && (w < args.Q) && (h < args.P) && (n < args.Nimg);
       const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
-      const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
+      return pix * (size_t)args.ldo + (size_t)nt * args.BN;
+    };
+    auto load_residual = [&](Vec8* dst, size_t off) {
+#pragma unroll
+      for (int i = 0; i < EPI_RES_VECS; ++i)
+        if (c_lo + 8 * i < c_hi) dst[i].raw = ldg_stream(args.residual + off + c_lo + 8 * i);
+    };
+    Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
+    const bool prefetch_res = !TF32 && args.residual != nullptr;
+    if (prefetch_res && pair_id < num_ptiles) {
+      bool v0;
+      int nt0;
+      const size_t off0 = unit_row(pair_id, v0, nt0);
+      if (v0) load_residual(rcur, off0);
+    }
+    for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
+      bool valid;
+      int nt;
+      const size_t off = unit_row(ct, valid, nt);
       bf16* orow = args.out + off;
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
 
-      // residual row prefetched before the accumulator wait (see conv_tc2h_kernel)
-      Vec8 rv[EPI_RES_VECS];
-      if (!TF32 && rrow && valid) {
-#pragma unroll
-        for (int i = 0; i < EPI_RES_VECS; ++i)
-          if (c_lo + 8 * i < c_hi) rv[i].raw = ldg_stream(rrow + c_lo + 8 * i);
-      }
-
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (prefetch_res && ct + num_pairs < num_ptiles) {   // next unit's residual row: in flight while this one drains
+        bool vn;
+        int ntn;
+        const size_t offn = unit_row(ct + num_pairs, vn, ntn);
+        if (vn) load_residual(rnext, offn);
+      }
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
 #pragma unroll
-      for (int ci = 0; ci < EPI_RES_VECS / 2; ++ci) {
+      for (int ci = 0; ci < EPI_MAX_CHUNKS; ++ci) {
         const int c = c_lo + 16 * ci;
         if (c >= c_hi) break;
+        const int ri = (2 * ci + 1 < EPI_RES_VECS) ? 2 * ci : 0;   // (a fused residual implies <= 5 chunks)
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -596,8 +620,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             if (rrow) {
               float rf[16];
-              rv[2 * ci].to_float(rf);
-              rv[2 * ci + 1].to_float(rf + 8);
+              rcur[ri].to_float(rf);
+              rcur[ri + 1].to_float(rf + 8);
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
             }
@@ -617,6 +641,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      if (prefetch_res) {
+#pragma unroll
+        for (int i = 0; i < EPI_RES_VECS; ++i) rcur[i] = rnext[i];
+      }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -841,36 +869,46 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
-    for (int ct = pair_id; ct < num_units; ct += num_pairs) {
-      const int nt = ct % args.n_ntiles;
+    auto unit_row = [&](int ct, int& nt) -> size_t {
+      nt = ct % args.n_ntiles;
       const int mt = ((ct / args.n_ntiles) * 2 + crank) * MT + t;
       const int w = (mt % args.tiles_w) * 8 + wi;
       const int h = ((mt / args.tiles_w) % args.tiles_h) * 16 + hi;
       const int n = mt / tiles_img;
       const size_t pix = ((size_t)n * args.P + h) * args.Q + w;
-      const size_t off = pix * (size_t)args.ldo + (size_t)nt * args.BN;
+      return pix * (size_t)args.ldo + (size_t)nt * args.BN;
+    };
+    auto load_residual = [&](Vec8* dst, size_t off) {
+#pragma unroll
+      for (int i = 0; i < EPI_RES_VECS; ++i)
+        if (c_lo + 8 * i < c_hi) dst[i].raw = ldg_stream(args.residual + off + c_lo + 8 * i);
+    };
+    Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
+    const bool prefetch_res = args.residual != nullptr;
+    if (prefetch_res && pair_id < num_units) {
+      int nt0;
+      load_residual(rcur, unit_row(pair_id, nt0));
+    }
+    for (int ct = pair_id; ct < num_units; ct += num_pairs) {
+      int nt;
+      const size_t off = unit_row(ct, nt);
       bf16* orow = args.out + off;
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
 
-      // The residual row of this thread (up to 128 columns = 16 vectors) is fetched BEFORE waiting for the
-      // accumulator: ncu (profiles/r02_*) showed the epilogue of the residual variants stalled on these loads
-      // (long-scoreboard, ~18 % of all samples) when each 16-column chunk loaded its own slice after tcgen05.ld.
-      Vec8 rv[EPI_RES_VECS];
-      if (rrow) {
-#pragma unroll
-        for (int i = 0; i < EPI_RES_VECS; ++i)
-          if (c_lo + 8 * i < c_hi) rv[i].raw = ldg_stream(rrow + c_lo + 8 * i);
-      }
-
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (prefetch_res && ct + num_pairs < num_units) {   // next unit's residual row: in flight while this one drains
+        int ntn;
+        load_residual(rnext, unit_row(ct + num_pairs, ntn));
+      }
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u + (uint32_t)(t * args.BN);
 #pragma unroll
-      for (int ci = 0; ci < EPI_RES_VECS / 2; ++ci) {
+      for (int ci = 0; ci < EPI_MAX_CHUNKS * 2; ++ci) {
         const int c = c_lo + 16 * ci;
         if (c >= c_hi) break;
+        const int ri = (2 * ci + 1 < EPI_RES_VECS) ? 2 * ci : 0;   // (a fused residual implies <= 5 chunks)
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -883,8 +921,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (rrow) {
           float rf[16];
-          rv[2 * ci].to_float(rf);
-          rv[2 * ci + 1].to_float(rf + 8);
+          rcur[ri].to_float(rf);
+          rcur[ri + 1].to_float(rf + 8);
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
         }
@@ -902,6 +940,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+      if (prefetch_res) {
+#pragma unroll
+        for (int i = 0; i < EPI_RES_VECS; ++i) rcur[i] = rnext[i];
+      }
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
     if (STATS) {
