@@ -460,6 +460,8 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.bias = bias;
   a.stats = stats;
   a.fin = fin;
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
+               "conv_tc2h: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, pw, HALO_PH, 1)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
@@ -593,6 +595,8 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.out = reinterpret_cast<bf16*>(out);
   a.residual = reinterpret_cast<const bf16*>(residual);
   a.bias = bias;
+  B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
+               "conv_tc: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   if (es == 4) {
     B200_REQUIRE(pair, "conv_tc (tf32): shape needs the SM-pair kernel (even pixel-tile count, Cout %% 32 == 0)");
     CUtensorMap tmA, tmB;

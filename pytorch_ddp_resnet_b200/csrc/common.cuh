@@ -89,6 +89,20 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per lane. The conv epilogues
+// own one output ROW per lane (the TMEM layout), so a warp access touches 32 different rows; with 16-byte
+// accesses every sector was requested twice (two instructions, each using half of it).
+__device__ __forceinline__ void ldg256_stream(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // counter-based RNG for dropout: Philox-2x32 rounds (one 32x32->64 multiply each) keyed by the seed,
 // counter = index of a group of four elements. One call yields four 16-bit uniforms, ~3 integer

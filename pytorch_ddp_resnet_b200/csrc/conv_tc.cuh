@@ -552,8 +552,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
     auto load_residual = [&](Vec8* dst, size_t off) {
 #pragma unroll
-      for (int i = 0; i < EPI_RES_VECS; ++i)
-        if (c_lo + 8 * i < c_hi) dst[i].raw = ldg_stream(args.residual + off + c_lo + 8 * i);
+      for (int i = 0; i < EPI_RES_VECS / 2; ++i)
+        if (c_lo + 16 * i < c_hi) ldg256_stream(args.residual + off + c_lo + 16 * i, dst[2 * i].raw, dst[2 * i + 1].raw);
     };
     Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
     const bool prefetch_res = !TF32 && args.residual != nullptr;
@@ -632,8 +632,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             Vec8 o0, o1;
             o0.from_float(f);
             o1.from_float(f + 8);
-            *reinterpret_cast<uint4*>(orow + c) = o0.raw;
-            *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+            stg256(orow + c, o0.raw, o1.raw);
           }
           if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
         }
@@ -880,8 +879,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     auto load_residual = [&](Vec8* dst, size_t off) {
 #pragma unroll
-      for (int i = 0; i < EPI_RES_VECS; ++i)
-        if (c_lo + 8 * i < c_hi) dst[i].raw = ldg_stream(args.residual + off + c_lo + 8 * i);
+      for (int i = 0; i < EPI_RES_VECS / 2; ++i)
+        if (c_lo + 16 * i < c_hi) ldg256_stream(args.residual + off + c_lo + 16 * i, dst[2 * i].raw, dst[2 * i + 1].raw);
     };
     Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
     const bool prefetch_res = args.residual != nullptr;
@@ -933,8 +932,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         Vec8 o0, o1;
         o0.from_float(f);
         o1.from_float(f + 8);
-        *reinterpret_cast<uint4*>(orow + c) = o0.raw;
-        *reinterpret_cast<uint4*>(orow + c + 8) = o1.raw;
+        stg256(orow + c, o0.raw, o1.raw);
         if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
       }
       tc_fence_before();
