@@ -245,7 +245,9 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
                 res = conv_wgrad(dy, x, R, S, stride, pad, want_dbias, algo, out, out_db)
         finally:
             _overlap["on"] = True
-        _overlap["keep"][x.device.index].append((dy, x, res))
+        # (a bias gradient that lives in a caller-owned slot is NOT kept: an extra reference would make autograd
+        #  clone it instead of adopting the slot as .grad)
+        _overlap["keep"][x.device.index].append((dy, x, res[0], None if out_db is not None else res[1]))
         return res
     N, H, W, C = x.shape
     Nd, P, Q, K = dy.shape
