@@ -425,13 +425,13 @@ static bool conv_use_halo() {
 }
 
 // Halo-reuse SM-pair launch (see conv_tc2h_kernel). MT pixel tiles per CTA share each filter stage.
-template <int KC, int MT, bool STATS>
+template <int KC, int MT, bool STATS, bool TAIL32 = false>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                             int wcols, const TapTable& taps, void* out, const void* residual,
                             const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
                             const EpiStatsFinal& fin, cudaStream_t st) {
   const int max_dyn = STATS ? 228352 - 6144 : 228352;   // STATS: 8 KB of static shared memory for the partial sums
-  B200_CUDA(ensure_max_smem<conv_tc2h_kernel<KC, MT, STATS>>(max_dyn));
+  B200_CUDA(ensure_max_smem<conv_tc2h_kernel<KC, MT, STATS, TAIL32>>(max_dyn));
   ConvHaloArgs a;
   memset(&a, 0, sizeof(a));
   a.tiles_w = Q / 8; a.tiles_h = P / 16;
@@ -462,9 +462,11 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.fin = fin;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
                "conv_tc2h: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA32, tmB32;
   if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, pw, HALO_PH, 1)) return rc;
   if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
+  if (int rc = make_tmap_nhwc(&tmA32, act, Nact, Ha, Wa, Cin, 32, pw, HALO_PH, 1)) return rc;   // tail block maps
+  if (int rc = make_tmap_2d(&tmB32, wmat, Cout, wcols, 32, BN / 2)) return rc;
   size_t dyn = 2 * MT * (size_t)a.patch_bytes + (size_t)a.bstages * a.bstage_bytes + 1024;
   dyn = std::max<size_t>(dyn, 120 * 1024);
   const int num_units = a.num_tiles / (2 * MT);
@@ -481,7 +483,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC, MT, STATS>, tmA, tmB, a));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2h_kernel<KC, MT, STATS, TAIL32>, tmA, tmB, tmA32, tmB32, a));
   B200_LAUNCH_CHECK("conv_tc2h_kernel");
   return 0;
 }
@@ -572,11 +574,16 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       static const int pw = std::max(10, std::min(16, env_int("B200_HALO_PW", 10)));
       const bool mt2 = mt_env == 2 && mt8x16 % 4 == 0 && 2 * BN <= 512 && (!residual || BN <= 8 * EPI_RES_VECS);
 #define B200_HALO_ARGS act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, residual, bias, Nimg, P, Q, BN, pw
+      // Cin = 64 n + 32 (the 160-channel layers): 64-channel blocks + one 32-channel tail block
+      static const int mixed_env = env_int("B200_HALO_MIXED", 1);
+      const bool mixed = mixed_env && !mt2 && Cin > 64 && Cin % 64 == 32;
       if (stats && !mt2 && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
         *stats_fused = true;
+        if (mixed) return launch_conv_tc2h<64, 1, true, true>(B200_HALO_ARGS, stats, fin, st);
         if (KC == 64) return launch_conv_tc2h<64, 1, true>(B200_HALO_ARGS, stats, fin, st);
         return launch_conv_tc2h<32, 1, true>(B200_HALO_ARGS, stats, fin, st);
       }
+      if (mixed) return launch_conv_tc2h<64, 1, false, true>(B200_HALO_ARGS, nullptr, fin, st);
       if (KC == 64)
         return mt2 ? launch_conv_tc2h<64, 2, false>(B200_HALO_ARGS, nullptr, fin, st)
                    : launch_conv_tc2h<64, 1, false>(B200_HALO_ARGS, nullptr, fin, st);

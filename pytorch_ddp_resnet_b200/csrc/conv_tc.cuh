@@ -699,11 +699,19 @@ struct ConvHaloArgs {
 // buffered when MT = 2, epilogue with 4 warps PER TILE). ncu on MT = 1: 330 MB per launch through the
 // L2->SM path, 236 MB of it the same filter tiles fetched once per tile pair; MT = 2 halves that but was
 // measured SLOWER (983 vs 1183 TFLOP/s at 160 channels): kept for experiments, default MT = 1.
-template <int KC, int MT, bool STATS>
+// TAIL32 (with KC = 64): input-channel counts of the form 64 n + 32 (the 160-channel WRN layers). The first n
+// K-blocks are 64 channels wide (128-byte rows, SWIZZLE_128B: ncu measured the tensor pipe at 98 % of its
+// instruction rate while active) and ONE last block holds the remaining 32 channels on 64-byte rows (SWIZZLE_64B,
+// 72 %): 80 % of the MMAs run at the fast rate instead of none (round 1 ran such layers entirely on 64-byte rows).
+// The tail block has its own tensor maps (tmA32 / tmB32: 32-channel boxes) and reuses the patch / filter slots.
+template <int KC, int MT, bool STATS, bool TAIL32 = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA32, const __grid_constant__ CUtensorMap tmB32,
                  const __grid_constant__ ConvHaloArgs args) {
+  static_assert(!TAIL32 || KC == 64, "the 32-channel tail block follows 64-channel blocks");
   constexpr int NBUF = (MT == 1) ? 2 : 1;   // accumulator sets
+  const int nblk = args.nkc + (TAIL32 ? 1 : 0);   // K-blocks per unit
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t pfull_bar[2], pempty_bar[2];
   __shared__ uint64_t bfull_bar[HALO_BSTAGES_MAX], bempty_bar[HALO_BSTAGES_MAX];
@@ -724,6 +732,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TAIL32) {
+      tma_prefetch_desc(&tmA32);
+      tma_prefetch_desc(&tmB32);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&pfull_bar[i], 1);
       mbar_init(&pempty_bar[i], 1);
@@ -760,18 +772,21 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       const int nt = ct % args.n_ntiles;
       const int mt0 = ((ct / args.n_ntiles) * 2 + crank) * MT;
-      for (int kc = 0; kc < args.nkc; ++kc) {
+      for (int kc = 0; kc < nblk; ++kc) {
+        const bool tail = TAIL32 && kc == args.nkc;          // the 32-channel block: half the bytes
+        const CUtensorMap* mapA = tail ? &tmA32 : &tmA;
+        const CUtensorMap* mapB = tail ? &tmB32 : &tmB;
         mbar_wait(&pempty_bar[ps], pph ^ 1);
         if (elect_one()) {
           const uint32_t pfull_leader = map_to_cta(smem_u32(&pfull_bar[ps]), 0);
-          if (leader) mbar_expect_tx(&pfull_bar[ps], 2u * MT * args.patch_tx_bytes);
+          if (leader) mbar_expect_tx(&pfull_bar[ps], (2u * MT * args.patch_tx_bytes) >> (tail ? 1 : 0));
 #pragma unroll
           for (int t = 0; t < MT; ++t) {
             const int mt = mt0 + t;
             const int w0 = (mt % args.tiles_w) * 8;
             const int h0 = ((mt / args.tiles_w) % args.tiles_h) * 16;
             const int n0 = mt / tiles_img;
-            tma_load_4d_2sm(smem + (size_t)ps * pslot_bytes + (size_t)t * args.patch_bytes, &tmA,
+            tma_load_4d_2sm(smem + (size_t)ps * pslot_bytes + (size_t)t * args.patch_bytes, mapA,
                             pfull_leader, kc * KC, w0 - 1, h0 - 1, n0);
           }
         }
@@ -783,10 +798,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t bfull_leader = map_to_cta(smem_u32(&bfull_bar[bs]), 0);
             const int t0 = tg * args.tpb;
             const int cnt = min(args.tpb, args.ntaps - t0);
-            if (leader) mbar_expect_tx(&bfull_bar[bs], 2u * (uint32_t)cnt * args.btile_bytes);
+            if (leader) mbar_expect_tx(&bfull_bar[bs], (2u * (uint32_t)cnt * args.btile_bytes) >> (tail ? 1 : 0));
             uint8_t* dst = bring + (size_t)bs * args.bstage_bytes;
             for (int j = 0; j < cnt; ++j)
-              tma_load_2d_2sm(dst + (size_t)j * args.btile_bytes, &tmB, bfull_leader,
+              tma_load_2d_2sm(dst + (size_t)j * args.btile_bytes, mapB, bfull_leader,
                               args.tap_wcol[t0 + j] + kc * KC, nt * args.BN + crank * bhalf);
           }
           __syncwarp();
@@ -800,6 +815,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = make_idesc_bf16(256, args.BN, 0, 0);
       const uint32_t bhi = smem_desc_hi(KMajorCfg<KC>::SBO, KMajorCfg<KC>::LAYOUT);
       const uint32_t ahi = smem_desc_hi((uint32_t)pw * KMajorCfg<KC>::ROW_BYTES, KMajorCfg<KC>::LAYOUT);
+      const uint32_t bhi32 = smem_desc_hi(KMajorCfg<32>::SBO, KMajorCfg<32>::LAYOUT);   // tail block: 64-byte rows
+      const uint32_t ahi32 = smem_desc_hi((uint32_t)pw * KMajorCfg<32>::ROW_BYTES, KMajorCfg<32>::LAYOUT);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t bring_base = smem_u32(bring);
       const uint32_t bstep = args.btile_bytes >> 4;
@@ -811,7 +828,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)as * 256u;
         uint32_t acc = 0;
-        for (int kc = 0; kc < args.nkc; ++kc) {
+        for (int kc = 0; kc < nblk; ++kc) {
+          const bool tail = TAIL32 && kc == args.nkc;
           mbar_wait(&pfull_bar[ps], pph);
           const uint32_t patch_lo = smem_desc_lo(smem_base + (uint32_t)ps * pslot_bytes, 16);
           for (int tg = 0; tg < args.ntg; ++tg) {
@@ -821,24 +839,41 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int t0 = tg * args.tpb;
               const int cnt = min(args.tpb, args.ntaps - t0);
               uint32_t blo = smem_desc_lo(bring_base + (uint32_t)bs * args.bstage_bytes, 16);
-              for (int j = 0; j < cnt; ++j) {
-                const uint32_t alo =
-                    patch_lo + (((uint32_t)args.tap_rowoff[t0 + j] * KMajorCfg<KC>::ROW_BYTES) >> 4);
+              if (!tail) {
+                for (int j = 0; j < cnt; ++j) {
+                  const uint32_t alo =
+                      patch_lo + (((uint32_t)args.tap_rowoff[t0 + j] * KMajorCfg<KC>::ROW_BYTES) >> 4);
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  const uint64_t bd = smem_desc_join(blo + 2 * k, bhi);
+                  for (int k = 0; k < KC / 16; ++k) {
+                    const uint64_t bd = smem_desc_join(blo + 2 * k, bhi);
 #pragma unroll
-                  for (int t = 0; t < MT; ++t)
-                    umma_bf16_ss_2sm(d_addr + (uint32_t)(t * args.BN),
-                                     smem_desc_join(alo + t * pstep + 2 * k, ahi), bd, idesc, acc);
-                  acc = 1u;
+                    for (int t = 0; t < MT; ++t)
+                      umma_bf16_ss_2sm(d_addr + (uint32_t)(t * args.BN),
+                                       smem_desc_join(alo + t * pstep + 2 * k, ahi), bd, idesc, acc);
+                    acc = 1u;
+                  }
+                  blo += bstep;
                 }
-                blo += bstep;
+              } else {
+                for (int j = 0; j < cnt; ++j) {
+                  const uint32_t alo =
+                      patch_lo + (((uint32_t)args.tap_rowoff[t0 + j] * KMajorCfg<32>::ROW_BYTES) >> 4);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const uint64_t bd = smem_desc_join(blo + 2 * k, bhi32);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t)
+                      umma_bf16_ss_2sm(d_addr + (uint32_t)(t * args.BN),
+                                       smem_desc_join(alo + t * pstep + 2 * k, ahi32), bd, idesc, acc);
+                    acc = 1u;
+                  }
+                  blo += bstep;
+                }
               }
               umma_commit_2sm_mcast(&bempty_bar[bs], 3);
               if (tg == args.ntg - 1) {
                 umma_commit_2sm_mcast(&pempty_bar[ps], 3);
-                if (kc == args.nkc - 1) umma_commit_2sm_mcast(&tfull_bar[as], 3);
+                if (kc == nblk - 1) umma_commit_2sm_mcast(&tfull_bar[as], 3);
               }
             }
             __syncwarp();
