@@ -158,20 +158,19 @@ class Conv2d(tc.nn.Module):
 
 class WeightPrepPlan:
     """Batched filter preparation for a whole model: persistent bf16 KRSC / CRSK buffers for every conv
-    and ONE kernel launch per step that refreshes all stale ones (instead of two launches per conv)."""
+    and ONE kernel launch per step that refreshes all stale ones (instead of two launches per conv).
+    prep_subset() refreshes a given group of convs in one launch (the graph-mode step does that per gradient
+    bucket, right after the bucket's SGD update, so the next forward finds every copy fresh)."""
 
     def __init__(self, convs):
         self.convs = list(convs)
         self.table = None
         self.ptrs = None
+        self.entries = None
+        self._subsets = {}
 
-    def refresh(self):
+    def _ensure_buffers(self):
         convs = self.convs
-        if not convs or not convs[0].weight.is_cuda:
-            return
-        keys = [c._key() for c in convs]
-        if all(c._cache is not None and c._cache[0] == k for c, k in zip(convs, keys)):
-            return
         ptrs = tuple(c.weight.data_ptr() for c in convs)
         if self.table is None or self.ptrs != ptrs:
             entries = []
@@ -184,9 +183,36 @@ class WeightPrepPlan:
             self.entries = entries
             self.table = ops.weight_prep_table(entries)
             self.ptrs = ptrs
+            self._subsets = {}
+
+    def refresh(self):
+        convs = self.convs
+        if not convs or not convs[0].weight.is_cuda:
+            return
+        keys = [c._key() for c in convs]
+        if all(c._cache is not None and c._cache[0] == k for c, k in zip(convs, keys)):
+            return
+        self._ensure_buffers()
         ops.weight_prep_multi(self.table, len(convs))
         for c, k, (_, wk, wt) in zip(convs, keys, self.entries):
             c._cache = (k, wk, wt)
+
+    def prep_subset(self, subset):
+        """Refreshes the bf16 copies of the convs in `subset` (one launch) and marks them fresh."""
+        subset = [c for c in subset if c.weight.is_cuda]
+        if not subset:
+            return
+        self._ensure_buffers()
+        index = {id(c): i for i, c in enumerate(self.convs)}
+        key = tuple(index[id(c)] for c in subset)
+        table = self._subsets.get(key)
+        if table is None:
+            table = ops.weight_prep_table([self.entries[i] for i in key])
+            self._subsets[key] = table
+        ops.weight_prep_multi(table, len(key))
+        for c, i in zip(subset, key):
+            _, wk, wt = self.entries[i]
+            c._cache = (c._key(), wk, wt)
 
 
 def conv_weight_grad(dw_krsc: torch.Tensor) -> torch.Tensor:

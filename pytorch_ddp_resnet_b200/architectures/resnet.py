@@ -114,11 +114,14 @@ class ResNet(tc.nn.Module):
                 with tc.no_grad():
                     m.weight.copy_(w)
 
+    def _ensure_prep_plan(self):
+        if self._prep_plan is None:
+            self._prep_plan = WeightPrepPlan(m for m in self.modules() if isinstance(m, Conv2d))
+        return self._prep_plan
+
     def forward(self, x):
         if x.is_cuda:  # refresh every stale bf16 filter copy of the model in one launch
-            if self._prep_plan is None:
-                self._prep_plan = WeightPrepPlan(m for m in self.modules() if isinstance(m, Conv2d))
-            self._prep_plan.refresh()
+            self._ensure_prep_plan().refresh()
         mods = list(self._architecture)
         i = 0
         while i < len(mods):

@@ -87,9 +87,12 @@ class FlatGradReducer:
     """Flat gradient buffer + bucketed, backward-overlapped NCCL all-reduce (mean) for one module."""
 
     def __init__(self, module: torch.nn.Module, device: torch.device, world: int,
-                 bucket_bytes: int = DEFAULT_BUCKET_BYTES, exchange: bool = True):
+                 bucket_bytes: int = DEFAULT_BUCKET_BYTES, exchange: bool = True, after_bucket=None):
+        """after_bucket(b, params): called on the communication stream right after bucket b's exchange (e.g. the
+        optimizer update of exactly those parameters, overlapped with the rest of backward)."""
         self.module, self.device, self.world = module, device, world
         self.exchange = exchange and world > 1
+        self.after_bucket = after_bucket
         params = [p for p in module.parameters() if p.requires_grad]
         self.params = params[::-1]
         offsets, owner, self.ranges = plan_buckets([p.numel() for p in self.params], bucket_bytes)
@@ -97,6 +100,9 @@ class FlatGradReducer:
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.slot = {id(p): self.flat[o:o + p.numel()] for p, o in zip(self.params, offsets)}
         self.bucket_of = {id(p): b for p, b in zip(self.params, owner)}
+        self.bucket_params = [[] for _ in self.ranges]
+        for p, b in zip(self.params, owner):
+            self.bucket_params[b].append(p)
         self.bucket_size = [0] * len(self.ranges)
         for b in owner:
             self.bucket_size[b] += 1
@@ -154,12 +160,15 @@ class FlatGradReducer:
 
     def _launch(self, b: int) -> None:
         self.launched[b] = True
-        if not self.exchange:
+        if not self.exchange and self.after_bucket is None:
             return
         lo, hi = self.ranges[b]
         if self.comm is None:   # host tensors (gloo): no streams, no AVG
-            torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.SUM)
-            self.flat[lo:hi].div_(self.world)
+            if self.exchange:
+                torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.SUM)
+                self.flat[lo:hi].div_(self.world)
+            if self.after_bucket is not None:
+                self.after_bucket(b, self.bucket_params[b])
             return
         cur = torch.cuda.current_stream(self.device)
         self.comm.wait_stream(cur)
@@ -167,16 +176,19 @@ class FlatGradReducer:
         if side is not None:
             self.comm.wait_stream(side)
         with torch.cuda.stream(self.comm):
-            torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.AVG)
+            if self.exchange:
+                torch.distributed.all_reduce(self.flat[lo:hi], op=torch.distributed.ReduceOp.AVG)
+            if self.after_bucket is not None:
+                self.after_bucket(b, self.bucket_params[b])
 
     def finish(self) -> None:
         """After backward: issues the buckets that never filled (parameters without a gradient) and makes
-        the current stream wait for every collective."""
+        the current stream wait for the communication stream."""
         self.active = False
         for b in range(len(self.ranges)):
             if not self.launched[b]:
                 self._launch(b)
-        if self.exchange and self.comm is not None:
+        if (self.exchange or self.after_bucket is not None) and self.comm is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm)
 
 
@@ -229,8 +241,21 @@ class GraphedTrainStep:
         self.local = classifier.module if self.is_ddp else classifier
         self.world = torch.distributed.get_world_size() if self.is_ddp else 1
         warmup = 3 if warmup is None else warmup
-        self.reducer = FlatGradReducer(self.local, self.device, self.world, bucket_bytes, exchange) \
-            if self.is_ddp else None
+        # Every gradient bucket is exchanged (N > 1), applied by the fused SGD and its filters re-cast to bf16 as
+        # soon as backward has produced it, on the communication stream, overlapped with the rest of backward: the
+        # 115 us SGD launch and the 75 us filter preparation of round 1 leave the critical path of the step.
+        self.bucket_step = hasattr(optimizer, "step_subset") and os.environ.get("B200_BUCKET_STEP", "1") != "0"
+        from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+        self.plan = None
+        if self.bucket_step and isinstance(self.local, ResNet):
+            self.local._ensure_prep_plan()
+            self.plan = self.local._prep_plan
+        self.reducer = FlatGradReducer(self.local, self.device, self.world, bucket_bytes, exchange,
+                                       after_bucket=self._after_bucket if self.bucket_step else None) \
+            if (self.is_ddp or self.bucket_step) else None
+        self._conv_of = {}
+        if self.plan is not None:
+            self._conv_of = {id(c.weight): c for c in self.plan.convs}
         ops.step_counter(self.device)  # must exist before capture (an in-capture alloc would re-zero it)
         with torch.cuda.device(self.device):
             ops.bn_accumulators(self.device)  # likewise: zero-filled once, outside the graph
@@ -254,7 +279,8 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             ops.tick(self.device)
             self.static_metrics = self._forward_backward_exchange(self.static_x, self.static_y)
-            self.optimizer.step()
+            if not self.bucket_step:
+                self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
         self.launches_per_step = _lib.launch_count() - l0  # kernels of ours inside one replay
         torch.cuda.synchronize(self.device)
@@ -264,8 +290,28 @@ class GraphedTrainStep:
         if self.eager_first:
             optimizer.state.clear()
         invalidate_weight_caches()
+        self._refresh_filters()   # the restored weights, re-cast into the buffers the graph reads
         if not was_training:
             classifier.eval()
+
+    def _after_bucket(self, b: int, params) -> None:
+        """On the communication stream, after bucket b's exchange: SGD update of its parameters, then the bf16
+        KRSC / CRSK copies of its conv filters for the NEXT forward (backward is done with this bucket's layers)."""
+        self.optimizer.step_subset(params)
+        if self.plan is not None:
+            convs = [self._conv_of[id(p)] for p in params if id(p) in self._conv_of]
+            self.plan.prep_subset(convs)
+
+    def _param_versions(self) -> int:
+        return sum(p._version for p in self.local.parameters())
+
+    def _refresh_filters(self) -> None:
+        """bf16 filter copies from the current master weights (eagerly, into the persistent buffers). Needed when
+        the weights were changed outside the captured step: the graph's forward contains no cast kernel."""
+        if self.plan is not None:
+            invalidate_weight_caches()
+            self.plan.refresh()
+        self._versions = self._param_versions()
 
     def _forward_backward_exchange(self, x, y) -> Dict[str, torch.Tensor]:
         m = compute_losses_and_metrics(logits=self.local(x), labels=y)
@@ -281,7 +327,8 @@ class GraphedTrainStep:
     def _eager(self, x, y) -> Dict[str, torch.Tensor]:
         """One un-captured optimisation step with the same maths as a replay."""
         m = self._forward_backward_exchange(x, y)
-        self.optimizer.step()
+        if not self.bucket_step:
+            self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
         return m
 
@@ -306,9 +353,13 @@ class GraphedTrainStep:
             self.eager_first = False
             out = self._eager(x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True))
             invalidate_weight_caches()
+            if self.plan is not None:
+                self._versions = self._param_versions()   # the eager step re-cast every filter it updated
             return out
         if hasattr(self.optimizer, "sync_lr"):
             self.optimizer.sync_lr()
+        if self.plan is not None and self._param_versions() != self._versions:
+            self._refresh_filters()   # someone changed the weights between two replays (load_state_dict, ...)
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()

@@ -43,13 +43,14 @@ class FusedSGD(torch.optim.SGD):
                 return (torch.empty((4, n), dtype=torch.int64).pin_memory(),
                         torch.empty((4, n), dtype=torch.int64, device=device))
             ring = {"slot": 0, "bufs": [pair() + (torch.cuda.Event(),) for _ in range(self._ring)],
-                    "used": [False] * self._ring, "capture": [pair() for _ in range(2)], "ncap": 0}
+                    "used": [False] * self._ring, "capture": [], "pair": pair}
             self._tables[key] = ring
         if torch.cuda.is_current_stream_capturing():
-            if ring["ncap"] >= len(ring["capture"]):
+            # every captured launch keeps its own table for the life of the graph (replays re-read it)
+            if len(ring["capture"]) >= 256:
                 raise RuntimeError("FusedSGD: too many CUDA-graph captures of the same parameter set")
-            host, dev = ring["capture"][ring["ncap"]]
-            ring["ncap"] += 1
+            ring["capture"].append(ring["pair"]())
+            host, dev = ring["capture"][-1]
             return host, dev, None
         s = ring["slot"]
         ring["slot"] = (s + 1) % self._ring
@@ -79,7 +80,13 @@ class FusedSGD(torch.optim.SGD):
             self._lr_tensor(gi, self.param_groups[gi], device)
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step_subset(self, params):
+        """The update of `params` only (one launch): GraphedTrainStep steps every gradient bucket as soon as its
+        exchange has finished, overlapped with the rest of backward, instead of all parameters at the end."""
+        return self.step(only={id(p) for p in params})
+
+    @torch.no_grad()
+    def step(self, closure=None, only=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -94,7 +101,7 @@ class FusedSGD(torch.optim.SGD):
                 raise NotImplementedError("FusedSGD: maximize=True is not supported")
             fresh, seasoned = [], []
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise RuntimeError("FusedSGD needs fp32 CUDA parameters (no CPU fallback)")
@@ -134,7 +141,7 @@ class FusedSGD(torch.optim.SGD):
                              lr_dev=self._lr_tensor(gi, group, device))
                 for p, _, _ in items:
                     torch.autograd.graph.increment_version(p)
-                self._keepalive = items  # grads copied above must outlive the launch
+                self._keepalive = getattr(self, "_keepalive", [])[-64:] + [items]  # grads copied above outlive the launch
         return loss
 
 
