@@ -241,10 +241,12 @@ class GraphedTrainStep:
         self.local = classifier.module if self.is_ddp else classifier
         self.world = torch.distributed.get_world_size() if self.is_ddp else 1
         warmup = 3 if warmup is None else warmup
-        # Every gradient bucket is exchanged (N > 1), applied by the fused SGD and its filters re-cast to bf16 as
-        # soon as backward has produced it, on the communication stream, overlapped with the rest of backward: the
-        # 115 us SGD launch and the 75 us filter preparation of round 1 leave the critical path of the step.
-        self.bucket_step = hasattr(optimizer, "step_subset") and os.environ.get("B200_BUCKET_STEP", "1") != "0"
+        # Experiment switch B200_BUCKET_STEP=1: every gradient bucket is exchanged (N > 1), applied by the fused SGD
+        # and its filters re-cast to bf16 as soon as backward has produced it, on the communication stream,
+        # overlapped with the rest of backward. MEASURED SLOWER on one B200 (5.16 against 5.04 ms/step, round 2): the
+        # SGD / cast grids flood every SM with short blocks while a persistent conv kernel (one 200 KB CTA per SM)
+        # is trying to get all 148 SMs, so the conv kernels start late. Default: one SGD launch after backward.
+        self.bucket_step = hasattr(optimizer, "step_subset") and os.environ.get("B200_BUCKET_STEP", "0") != "0"
         from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
         self.plan = None
         if self.bucket_step and isinstance(self.local, ResNet):
