@@ -213,10 +213,12 @@ int b200_avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, 
                      b200_stream_t stream);
 int b200_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int k, int stride, int pad,
                      b200_stream_t stream);
-int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride, int pad,
-                     b200_stream_t stream);
-int b200_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W,
-                     int C, int k, int stride, int pad, b200_stream_t stream);
+/* argmax (may be NULL in eval): one byte per output element = window position r*k + s of the first maximum in
+ * row-major scan order (torch's max_pool2d_with_indices rule); the backward pass needs only dy and argmax. */
+int b200_maxpool_fwd(const void* x, void* y, void* argmax, int N, int H, int W, int C, int k, int stride,
+                     int pad, b200_stream_t stream);
+int b200_maxpool_bwd(const void* dy, const void* argmax, void* dx, int N, int H, int W, int C, int k,
+                     int stride, int pad, b200_stream_t stream);
 
 /* ---- classifier head (resnet.py:117-120; metrics.py:10-29) ---------------------------------- */
 /* logits[B,O] (bf16) = bf16(x[B,I] (bf16) . bf16(w[O,I])^T + bf16(b[O])) */

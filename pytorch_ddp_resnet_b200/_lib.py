@@ -48,8 +48,8 @@ SIGNATURES = {
     "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_avgpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
     "b200_avgpool_bwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
-    "b200_maxpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),
-    "b200_maxpool_bwd": (c_int, [_P, _P, _P, _P] + [c_int] * 7 + [_P]),
+    "b200_maxpool_fwd": (c_int, [_P, _P, _P] + [c_int] * 7 + [_P]),
+    "b200_maxpool_bwd": (c_int, [_P, _P, _P] + [c_int] * 7 + [_P]),
     "b200_linear_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_linear_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_ce_topk": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),

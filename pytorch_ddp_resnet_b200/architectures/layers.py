@@ -392,10 +392,12 @@ class PoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k: int, stride: int, pad: int, is_max: bool):
         xh = as_nhwc(x)
-        y = ops.maxpool_fwd(xh, k, stride, pad) if is_max else ops.avgpool_fwd(xh, k, stride, pad)
         ctx.cfg = (k, stride, pad, is_max, tuple(xh.shape))
-        if is_max and xh.dtype != torch.float32:
-            ctx.save_for_backward(xh, y)
+        if is_max and xh.dtype != torch.float32 and x.requires_grad:
+            y, argmax = ops.maxpool_fwd(xh, k, stride, pad, want_argmax=True)
+            ctx.save_for_backward(argmax)   # 1 byte per output element; neither x nor y is kept for backward
+        else:
+            y = ops.maxpool_fwd(xh, k, stride, pad) if is_max else ops.avgpool_fwd(xh, k, stride, pad)
         return as_nchw_view(y)
 
     @staticmethod
@@ -403,8 +405,8 @@ class PoolFn(torch.autograd.Function):
         k, stride, pad, is_max, shape = ctx.cfg
         g = grad_nhwc(gy)
         if is_max:
-            xh, y = ctx.saved_tensors
-            dx = ops.maxpool_bwd(g, xh, y, k, stride, pad)
+            (argmax,) = ctx.saved_tensors
+            dx = ops.maxpool_bwd(g, argmax, shape, k, stride, pad)
         else:
             dx = ops.avgpool_bwd(g, shape, k, stride, pad)
         return as_nchw_view(dx), None, None, None, None

@@ -71,6 +71,8 @@ static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Experiment switches are environment variables read ONCE per process: every use below is
+// a function-local `static const`, so no launch ever calls getenv.
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -330,13 +332,8 @@ static bool use_tc(int algo, int pass, int N, int H, int W, int C, int K, int R,
 
 static int conv_cluster_size() {
   // B200_CONV_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing one multicast filter tile
-  static int cs = 0;
-  if (cs == 0) {
-    const char* e = getenv("B200_CONV_CLUSTER");
-    cs = e ? atoi(e) : 2;
-    if (cs != 1 && cs != 2 && cs != 4) cs = 2;
-  }
-  return cs;
+  static const int v = env_int("B200_CONV_CLUSTER", 2);
+  return (v == 1 || v == 2 || v == 4) ? v : 2;
 }
 
 template <int KC, int CS>
@@ -386,7 +383,8 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
   // iteration), as long as three stages still fit
   const int budget = max_dyn - 1024;
   int gblk = std::max(1, 8 / (int)(KC * ES / 32));
-  if (const char* e = getenv("B200_CONV_GBLK")) gblk = std::max(1, atoi(e));
+  static const int gblk_env = env_int("B200_CONV_GBLK", 0);
+  if (gblk_env > 0) gblk = gblk_env;
   gblk = std::min(gblk, a.taps.n * a.nkc);
   while (gblk > 1 && budget / (int)(gblk * a.block_bytes) < 3) --gblk;
   a.gblk = gblk;
@@ -416,11 +414,7 @@ static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvT
 
 static bool conv_use_halo() {
   // B200_CONV_HALO=0 disables the halo-reuse kernel (3x3 / stride 1 / pad 1 layers fall back to conv_tc2)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_CONV_HALO");
-    v = e ? (atoi(e) != 0) : 1;
-  }
+  static const int v = env_int("B200_CONV_HALO", 1);
   return v != 0;
 }
 
@@ -446,7 +440,8 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   const int budget = max_dyn - 1024 - 2 * MT * (int)a.patch_bytes;
   // taps per filter stage: all 9 when three such stages fit (>= 18 MMAs per barrier round trip), else 3
   a.tpb = (budget / (int)(taps.n * a.btile_bytes) >= 3) ? taps.n : 3;
-  if (const char* e = getenv("B200_HALO_TPB")) a.tpb = std::max(1, std::min(atoi(e), taps.n));
+  static const int tpb_env = env_int("B200_HALO_TPB", 0);
+  if (tpb_env > 0) a.tpb = std::min(tpb_env, taps.n);
   a.ntg = (taps.n + a.tpb - 1) / a.tpb;
   a.bstage_bytes = (uint32_t)a.tpb * a.btile_bytes;
   a.bstages = std::min(HALO_BSTAGES_MAX, budget / (int)a.bstage_bytes);
@@ -490,11 +485,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
 
 static bool conv_use_pair() {
   // B200_CONV_PAIR=0 disables the cta_group::2 kernel (falls back to the single-CTA kernel)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_CONV_PAIR");
-    v = e ? (atoi(e) != 0) : 1;
-  }
+  static const int v = env_int("B200_CONV_PAIR", 1);
   return v != 0;
 }
 
@@ -888,13 +879,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
 
 static int wgrad_cluster_size() {
   // B200_WGRAD_CLUSTER = 1 | 2 | 4 (default 2): CTAs per cluster sharing the multicast dY slabs
-  static int cs = 0;
-  if (cs == 0) {
-    const char* e = getenv("B200_WGRAD_CLUSTER");
-    cs = e ? atoi(e) : 1;  // measured: no gain from multicasting dY (round 1), default off
-    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
-  }
-  return cs;
+  static const int v = env_int("B200_WGRAD_CLUSTER", 1);  // measured: no gain from multicasting dY (round 1)
+  return (v == 1 || v == 2 || v == 4) ? v : 1;
 }
 
 static int wgrad_mtiles_per_cta() {
@@ -902,13 +888,8 @@ static int wgrad_mtiles_per_cta() {
   // Measured in round 1 (after the producer's index math was hoisted): two tiles with 128-pixel stages
   // reach 928 / 902 TFLOP/s at C = 160 / 320 against 818 / 751 with one tile (28 % fewer bytes per MMA
   // through the TMA/L2 path), but 692 against 720 at C = 640, hence the auto rule in run_wgrad_tc.
-  static int mt = -1;
-  if (mt < 0) {
-    const char* e = getenv("B200_WGRAD_MT");
-    mt = e ? atoi(e) : 0;
-    if (mt < 0 || mt > 2) mt = 0;
-  }
-  return mt;
+  static const int v = env_int("B200_WGRAD_MT", 0);
+  return (v < 0 || v > 2) ? 0 : v;
 }
 
 template <int SL, int CS, int MT, bool TF32 = false>
@@ -918,7 +899,8 @@ static int launch_wgrad_tc(const CUtensorMap& tmX, const CUtensorMap& tmDy, Wgra
   B200_CUDA(ensure_max_smem<wgrad_tc_kernel<SL, CS, MT, TF32>>(max_dyn));
   a.stage_bytes = (uint32_t)(MT * (128 / SL) + a.nb) * a.slab_bytes;
   a.stages = std::min<int>(8, (max_dyn - 1024) / (int)a.stage_bytes);
-  if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
+  static const int stages_env = env_int("B200_WGRAD_STAGES", 0);
+  if (stages_env > 0) a.stages = std::max(2, std::min(a.stages, stages_env));
   B200_REQUIRE(a.stages >= 2, "wgrad_tc: tile does not fit in shared memory");
   a.tmem_cols = 32;
   while (a.tmem_cols < (MT - 1) * 256 + a.BN) a.tmem_cols *= 2;
@@ -975,19 +957,16 @@ static int pick_wgrad_splits(int cols, int num_ptiles, int fixed_units) {
     const double cost = (double)waves * (per + fixed_units) * (1.0 + 0.001 * sp);  // ties: fewer atomics
     if (cost < best_cost) { best_cost = cost; best = sp; }
   }
-  if (const char* e = getenv("B200_WGRAD_SPLITS")) best = std::max(1, std::min(atoi(e), num_ptiles));
+  static const int splits_env = env_int("B200_WGRAD_SPLITS", 0);
+  if (splits_env > 0) best = std::min(splits_env, num_ptiles);
   const int per = (num_ptiles + best - 1) / best;
   return (num_ptiles + per - 1) / per;
 }
 
 static bool wgrad_use_halo() {
   // B200_WGRAD_HALO=0 falls back to the one-window-per-slab kernel
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_WGRAD_HALO");
-    v = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  return v == 1;
+  static const int v = env_int("B200_WGRAD_HALO", 1);
+  return v != 0;
 }
 
 // Halo-reuse SM-pair wgrad (3x3, stride 1, pad 1): see wgrad_tc2h_kernel. Returns -1 when the shape is
@@ -1003,8 +982,8 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   else return -1;
   const int BN = pick_bn(K, 32, 160);
   if (BN <= 0) return -1;
-  int pw = 10;
-  if (const char* e = getenv("B200_WGRAD_PW")) pw = (atoi(e) == 16) ? 16 : 10;  // box bytes stay 1 KB multiples
+  static const int pw_env = env_int("B200_WGRAD_PW", 10);
+  const int pw = (pw_env == 16) ? 16 : 10;  // box bytes stay 1 KB multiples
   WgradHaloArgs a;
   memset(&a, 0, sizeof(a));
   a.bh = bh; a.bn = bn; a.pw = pw;
@@ -1020,7 +999,8 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   a.stage_bytes = 4 * a.box_bytes + (uint32_t)a.nbh * a.slab_bytes;
   const int max_dyn = 228352;
   a.stages = std::min<int>(WGH_STAGES_MAX, (max_dyn - 1024) / (int)a.stage_bytes);
-  if (const char* e = getenv("B200_WGRAD_STAGES")) a.stages = std::max(2, std::min(a.stages, atoi(e)));
+  static const int stages_env = env_int("B200_WGRAD_STAGES", 0);
+  if (stages_env > 0) a.stages = std::max(2, std::min(a.stages, stages_env));
   if (a.stages < 2) return -1;
   a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles, 5);
   for (int t = 0; t < 9; ++t) a.wcol[t] = taps.wcol[t];
@@ -1097,19 +1077,17 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   // slab width: 32 channels (64-byte TMA rows, SWIZZLE_64B) or 16; 64-channel slabs (SWIZZLE_128B, with
   // partial last slabs) are implemented and tested but were not faster (round 1), B200_WGRAD_SLAB=64
   int SL = (C % 32 == 0 && K % 32 == 0) ? 32 : 16;
-  if (const char* e = getenv("B200_WGRAD_SLAB")) {
-    const int v = atoi(e);
-    if ((v == 16 || v == 32) && C % v == 0 && K % v == 0) SL = v;
-    if (v == 64 && C >= 64 && K >= 64) SL = 64;
-  }
+  static const int slab_env = env_int("B200_WGRAD_SLAB", 0);
+  if ((slab_env == 16 || slab_env == 32) && C % slab_env == 0 && K % slab_env == 0) SL = slab_env;
+  if (slab_env == 64 && C >= 64 && K >= 64) SL = 64;
   int BN = pick_bn(K, 16, 160);
   if (SL < 64) BN = pick_bn(K, SL, 160);
   B200_REQUIRE(BN > 0, "wgrad_tc: no legal N tile for K=%d", K);
   const int cs = wgrad_cluster_size();
   int mt = wgrad_mtiles_per_cta();
   if (mt == 0) mt = (C <= 320) ? 2 : 1;
-  int px_cap = 128;
-  if (const char* e = getenv("B200_WGRAD_PX")) px_cap = (atoi(e) == 64) ? 64 : 128;
+  static const int px_env = env_int("B200_WGRAD_PX", 128);
+  const int px_cap = (px_env == 64) ? 64 : 128;
   TilePlan t = plan_tiles_mult16(N, P, Q, px_cap);
   if (t.rows_valid % 16 != 0 && mt == 2) { mt = 1; t = plan_tiles_mult16(N, P, Q, 128); }
   B200_REQUIRE(t.rows_valid % 16 == 0, "wgrad_tc: pixel tile of %d rows is not a multiple of 16",
@@ -1645,20 +1623,20 @@ extern "C" int b200_avgpool_bwd(const void* dy, void* dx, int N, int H, int W, i
   return 0;
 }
 
-extern "C" int b200_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int k, int stride,
-                                int pad, b200_stream_t stream) {
-  B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1, "maxpool_fwd: bad arguments");
+extern "C" int b200_maxpool_fwd(const void* x, void* y, void* argmax, int N, int H, int W, int C, int k,
+                                int stride, int pad, b200_stream_t stream) {
+  B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1 && k * k <= 255, "maxpool_fwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  launch_k(maxpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, d);
+  launch_k(maxpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, reinterpret_cast<uint8_t*>(argmax), d);
   B200_LAUNCH_CHECK("maxpool_fwd_kernel");
   return 0;
 }
 
-extern "C" int b200_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H,
-                                int W, int C, int k, int stride, int pad, b200_stream_t stream) {
-  B200_REQUIRE(dy && x && y && dx && stride >= 1 && C % 8 == 0, "maxpool_bwd: bad arguments");
+extern "C" int b200_maxpool_bwd(const void* dy, const void* argmax, void* dx, int N, int H, int W, int C, int k,
+                                int stride, int pad, b200_stream_t stream) {
+  B200_REQUIRE(dy && argmax && dx && stride >= 1 && C % 8 == 0, "maxpool_bwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
-  launch_k(maxpool_bwd_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)dy, (const bf16*)x, (const bf16*)y, (bf16*)dx, d);
+  launch_k(maxpool_bwd_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)dy, reinterpret_cast<const uint8_t*>(argmax), (bf16*)dx, d);
   B200_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;
 }

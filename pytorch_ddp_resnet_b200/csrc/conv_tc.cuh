@@ -51,8 +51,6 @@ struct ConvTcArgs {
   uint32_t stage_bytes;
   uint32_t a_bytes;                 // 128 * KC * 2
   uint32_t tx_bytes;                // bytes landed per K-block (per CTA)
-  int probe_rowoff;                 // PROBE ONLY: A box loaded `rowoff` pixels early, descriptor starts rowoff rows in
-  int probe_baseoff;                // PROBE ONLY: value of the descriptor's base_offset field
   int gblk;                         // K-blocks per pipeline stage (SM-pair kernel)
   int cstride;                      // conv stride: window origin = output pixel * cstride + tap displacement
                                     // (stride 2 reads every other pixel through the TMA map's elementStrides)
@@ -237,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* a_dst = smem + (size_t)s * args.stage_bytes;
             uint8_t* b_dst = a_dst + args.a_bytes;
             mbar_expect_tx(&full_bar[s], args.tx_bytes);
-            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw - args.probe_rowoff, ch, cn);
+            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * KC, cw, ch, cn);
             if (CS == 1) {
               tma_load_2d(b_dst, &tmB, &full_bar[s], wc + kc * KC, nt * args.BN);
             } else {
@@ -269,9 +267,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_base + (uint32_t)s * args.stage_bytes;
-          const uint32_t alo = smem_desc_lo(a_addr + (uint32_t)args.probe_rowoff * KMajorCfg<KC>::ROW_BYTES, 16);
+          const uint32_t alo = smem_desc_lo(a_addr, 16);
           const uint32_t blo = smem_desc_lo(a_addr + args.a_bytes, 16);
-          const uint32_t ahi = dhi | ((uint32_t)(args.probe_baseoff & 7) << 17);  // base_offset: bits [49,52)
+          const uint32_t ahi = dhi;
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
             umma_bf16_ss(d_addr, smem_desc_join(alo + 2 * k, ahi), smem_desc_join(blo + 2 * k, dhi),
@@ -1251,7 +1249,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // ~50 delivered). Here one TMA box per (filter row r, chunk) holds the pixel tile widened by the
 // horizontal halo: [bn*bh = 16 pixel rows][PW columns w0-1 ..][32 channels], and the three taps
 // s = 0..2 of that filter row are the SAME box read through descriptors that start s pixel rows (64 B)
-// later (UMMA swizzling follows absolute shared-memory address bits, tools/probe_rowoff.py). The
+// later (UMMA swizzling follows absolute shared-memory address bits: probed on the hardware in round 1). The
 // 8-pixel groups of the MMA K dimension are image rows, so their stride (SBO) is PW pixel rows.
 //
 // Work decomposition: a "combo" is (chunk, r); a column is 4 combos = the 4 channel slabs of a

@@ -92,8 +92,11 @@ def _drop_pending_stats(device: torch.device) -> None:
     _pending_stats.pop(_accum_key(device), None)
 
 
+_FUSED_BN_STATS = os.environ.get("B200_FUSED_BN_STATS", "1") != "0"   # experiment switch, read once at import
+
+
 def fused_bn_stats_enabled() -> bool:
-    return os.environ.get("B200_FUSED_BN_STATS", "1") != "0"
+    return _FUSED_BN_STATS
 
 
 def tick(device: torch.device) -> None:
@@ -102,9 +105,12 @@ def tick(device: torch.device) -> None:
 
 
 
+_CONV_ALGO = _ALGO_NAMES[os.environ.get("B200_CONV_ALGO", "auto")]   # experiment switch, read once at import
+
+
 def conv_algo() -> int:
     """Conv algorithm from B200_CONV_ALGO (auto | direct | tc); 'auto' uses tcgen05 when it can."""
-    return _ALGO_NAMES[os.environ.get("B200_CONV_ALGO", "auto")]
+    return _CONV_ALGO
 
 
 def _stream() -> int:
@@ -454,7 +460,7 @@ def upsample_add_(dx, g, Cg: Optional[int] = None):
 # --------------------------------------------------------------------------------------------------
 # pooling
 # --------------------------------------------------------------------------------------------------
-def _pool(name, x, k, stride, pad):
+def _pool(name, x, k, stride, pad, want_argmax: bool = False):
     N, H, W, C = x.shape
     P, Q = _out_hw(H, W, k, k, stride, pad)
     if x.dtype == torch.float32:
@@ -465,6 +471,10 @@ def _pool(name, x, k, stride, pad):
         return y
     _check_act(x, name)
     y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=x.device)
+    if name == "b200_maxpool_fwd":
+        am = torch.empty((N, P, Q, C), dtype=torch.uint8, device=x.device) if want_argmax else None
+        _lib.call(name, x.data_ptr(), y.data_ptr(), _p(am), N, H, W, C, k, stride, pad, _stream())
+        return (y, am) if want_argmax else y
     _lib.call(name, x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, _stream())
     return y
 
@@ -473,8 +483,9 @@ def avgpool_fwd(x, k, stride, pad):
     return _pool("b200_avgpool_fwd", x, k, stride, pad)
 
 
-def maxpool_fwd(x, k, stride, pad):
-    return _pool("b200_maxpool_fwd", x, k, stride, pad)
+def maxpool_fwd(x, k, stride, pad, want_argmax: bool = False):
+    """want_argmax: also return the uint8 argmax positions that maxpool_bwd consumes -> (y, argmax)."""
+    return _pool("b200_maxpool_fwd", x, k, stride, pad, want_argmax)
 
 
 def avgpool_bwd(dy, in_shape, k, stride, pad):
@@ -485,12 +496,13 @@ def avgpool_bwd(dy, in_shape, k, stride, pad):
     return dx
 
 
-def maxpool_bwd(dy, x, y, k, stride, pad):
+def maxpool_bwd(dy, argmax, in_shape, k, stride, pad):
     _check_act(dy, "maxpool_bwd.dy")
-    N, H, W, C = x.shape
-    dx = torch.empty_like(x)
-    _lib.call("b200_maxpool_bwd", dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), N, H, W, C, k,
-              stride, pad, _stream())
+    N, H, W, C = in_shape
+    assert argmax.dtype == torch.uint8 and argmax.shape == dy.shape and argmax.is_contiguous()
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    _lib.call("b200_maxpool_bwd", dy.data_ptr(), argmax.data_ptr(), dx.data_ptr(), N, H, W, C, k, stride, pad,
+              _stream())
     return dx
 
 

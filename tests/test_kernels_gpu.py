@@ -364,11 +364,17 @@ def test_pools(k, s, p, H):
     assert rel_l2(nhwc(dx), xa.grad) < 8e-3
     xm = nhwc(x).float().contiguous().requires_grad_(True)
     refm = F.max_pool2d(xm, k, s, p)
-    ym = ops.maxpool_fwd(x, k, s, p)
-    assert torch.equal(nhwc(ym).float(), refm)
+    ym, am = ops.maxpool_fwd(x, k, s, p, want_argmax=True)
+    assert torch.equal(nhwc(ym).float(), refm) and torch.equal(ops.maxpool_fwd(x, k, s, p), ym)
     refm.backward(nhwc(dy).float().contiguous())
-    dxm = ops.maxpool_bwd(dy, x, ym, k, s, p)
+    dxm = ops.maxpool_bwd(dy, am, tuple(x.shape), k, s, p)
     assert rel_l2(nhwc(dxm), xm.grad) < 4e-3
+    # ties (bf16 inputs collide often): the FIRST maximum in scan order takes the gradient, like torch
+    xt = torch.randint(0, 3, x.shape, device="cuda").bfloat16()
+    xtm = nhwc(xt).float().contiguous().requires_grad_(True)
+    F.max_pool2d(xtm, k, s, p).backward(nhwc(dy).float().contiguous())
+    _, amt = ops.maxpool_fwd(xt, k, s, p, want_argmax=True)
+    assert rel_l2(nhwc(ops.maxpool_bwd(dy, amt, tuple(xt.shape), k, s, p)), xtm.grad) < 4e-3
 
 
 def test_linear_and_ce():
