@@ -71,10 +71,11 @@ size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int C, int K, 
                                    int stride, int pad, int algo);
 
 /* y = bf16( conv(x, w) [+ bias] ) ; if residual: y = bf16(y + residual)  (residual add of
- * residual_block.py:96,212 fused into the epilogue). bias (fp32 [K]) and residual may be NULL. */
+ * residual_block.py:96,212 fused into the epilogue); if relu: y = max(y, 0) last (evaluation with the
+ * following batch norm folded into w / bias, see utils/fold_util.py). bias (fp32 [K]) and residual may be NULL. */
 int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias, const void* residual,
                       void* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
-                      int algo, void* ws, size_t ws_bytes, b200_stream_t stream);
+                      int relu, int algo, void* ws, size_t ws_bytes, b200_stream_t stream);
 
 /* b200_conv2d_fprop that ALSO computes the batch statistics of its output for the batch norm that follows a
  * conv in the reference (residual_block.py:69-98), so that BN needs no pass of its own over y. Per output
@@ -115,7 +116,7 @@ int b200_conv2d_tf32_supported(int pass, int N, int H, int W, int C, int K, int 
 size_t b200_conv2d_tf32_workspace_bytes(int N, int H, int W, int C, int K, int R, int S, int stride, int pad);
 int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias, const float* residual,
                            float* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
-                           void* ws, size_t ws_bytes, b200_stream_t stream);
+                           int relu, void* ws, size_t ws_bytes, b200_stream_t stream);
 int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx, int N, int H,
                            int W, int C, int K, int R, int S, int stride, int pad, b200_stream_t stream);
 int b200_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw_krsc, int N, int H, int W, int C, int K,

@@ -29,7 +29,7 @@ SIGNATURES = {
     "b200_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "b200_weight_prep_multi": (c_int, [_P, c_int, _P]),
     "b200_conv2d_workspace_bytes": (c_size_t, [c_int] + _CONV_DIMS + [c_int]),
-    "b200_conv2d_fprop": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
+    "b200_conv2d_fprop": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, c_int, _P, c_size_t, _P]),
     "b200_conv2d_fprop_stats": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P, c_size_t,
                                         c_float, _P, _P, _P]),
     "b200_bn_running_update": (c_int, [_P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
@@ -58,7 +58,7 @@ SIGNATURES = {
     "b200_tick": (c_int, [_P, _P]),
     "b200_conv2d_tf32_supported": (c_int, [c_int] + _CONV_DIMS),
     "b200_conv2d_tf32_workspace_bytes": (c_size_t, _CONV_DIMS),
-    "b200_conv2d_fprop_tf32": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [_P, c_size_t, _P]),
+    "b200_conv2d_fprop_tf32": (c_int, [_P, _P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
     "b200_nchw_to_nhwc_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_bn_act_fwd_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_float, _P, _P, _P, c_int,
                                     c_int, c_int, _P]),

@@ -51,6 +51,14 @@ def require_forward_only(training: bool) -> None:
                         "evaluation.py:32-39); call .eval() or train in the default bf16 mode")
 
 
+def conv_forward_with(c, a, w, **kw):
+    """Convolution with the geometry of module `c` and an explicit filter `w` ([K,R,S,C], bf16 or fp32 matching
+    the activation): used with batch-norm-folded filters in evaluation."""
+    if a.dtype == torch.float32:
+        return ops.conv_fprop_tf32(a, w, c.stride, c.padding, **kw)
+    return ops.conv_fprop(a, w, c.stride, c.padding, **kw)
+
+
 def conv_forward(c, a, **kw):
     """One convolution of module `c` on activation `a` in the precision the activation carries: bf16 ->
     the bf16 tcgen05 kernels on the cached bf16 filter copy; fp32 -> kind::tf32 on the fp32 master filter."""

@@ -21,8 +21,9 @@ from pytorch_ddp_resnet_b200 import ops, _lib
 from pytorch_ddp_resnet_b200._lib import B200Error
 from pytorch_ddp_resnet_b200.architectures.layers import (
     Conv2d, BatchNorm2d, ReLU, Dropout, AvgPool2d, as_nhwc, as_nchw_view, grad_nhwc, conv_weight_grad,
-    next_dropout_seed, conv_forward, require_forward_only,
+    next_dropout_seed, conv_forward, conv_forward_with, require_forward_only,
 )
+from pytorch_ddp_resnet_b200.utils.fold_util import folded_filter
 
 
 class _BlockFn(torch.autograd.Function):
@@ -67,6 +68,29 @@ class _BlockFn(torch.autograd.Function):
 
         saved_in, saved_act, saved_conv, stats, masks = [], [], [], [], []
         h = xh
+        if not training and ops.get_fold_bn():
+            # evaluation with every foldable batch norm merged into the conv in front of it (utils/fold_util.py)
+            if preact:
+                a = ops.bn_act_fwd(h, relu=True, **bn_args(0, h))
+                for j, c in enumerate(convs):
+                    if j < n - 1:      # conv_j -> norm_{j+1} -> ReLU in ONE conv launch
+                        w, b = folded_filter(c, norms[j + 1], f32)
+                        a = conv_forward_with(c, a, w, bias=b, relu=True)
+                    elif skip_mode == _lib.SKIP_SAME:
+                        out = conv_forward(c, a, residual=skip)
+                    else:
+                        out = ops.bn_act_fwd(conv_forward(c, a), relu=False, skip=skip, skip_mode=skip_mode)
+            else:
+                for j, c in enumerate(convs):
+                    w, b = folded_filter(c, norms[j], f32)
+                    if j < n - 1:
+                        h = conv_forward_with(c, h, w, bias=b, relu=True)
+                    elif skip_mode == _lib.SKIP_SAME:
+                        out = conv_forward_with(c, h, w, bias=b, residual=skip, relu=True)
+                    else:
+                        out = ops.bn_act_fwd(conv_forward_with(c, h, w, bias=b), relu=True, skip=skip,
+                                             skip_mode=skip_mode)
+            return as_nchw_view(out)
         if preact:
             for j, c in enumerate(convs):
                 st = bn_args(j, h)

@@ -11,9 +11,12 @@ from typing import List, Tuple
 
 import torch as tc
 
+from pytorch_ddp_resnet_b200 import ops
 from pytorch_ddp_resnet_b200.architectures.layers import (
     Conv2d, BatchNorm2d, ReLU, Linear, AvgPool2d, MaxPool2d, TopConvFn, BnActFn, WeightPrepPlan,
+    as_nhwc, as_nchw_view, conv_forward_with,
 )
+from pytorch_ddp_resnet_b200.utils.fold_util import folded_filter
 from pytorch_ddp_resnet_b200.architectures.residual_block import (
     ResidualBlock, BottleneckResidualBlock,
 )
@@ -126,6 +129,15 @@ class ResNet(tc.nn.Module):
         i = 0
         while i < len(mods):
             m = mods[i]
+            if (not self.training and ops.get_fold_bn() and isinstance(m, ConvStem) and i + 1 < len(mods)
+                    and isinstance(mods[i + 1], BatchNorm2d)):
+                # evaluation: a top-level conv directly followed by `n [a]` runs as ONE conv (utils/fold_util.py)
+                xh = as_nhwc(x)
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], ReLU)
+                w, b = folded_filter(m, mods[i + 1], xh.dtype == tc.float32)
+                x = as_nchw_view(conv_forward_with(m, xh, w, bias=b, relu=relu))
+                i += 3 if relu else 2
+                continue
             if isinstance(m, BatchNorm2d) and i + 1 < len(mods) and isinstance(mods[i + 1], ReLU):
                 x = BnActFn.apply(x, m.weight, m.bias, m, True)  # fused `n a`
                 i += 2

@@ -418,6 +418,8 @@ static bool conv_use_halo() {
   return v != 0;
 }
 
+static thread_local int g_halo_relu = 0;   // epilogue ReLU flag of the halo launch being prepared by this thread
+
 // Halo-reuse SM-pair launch (see conv_tc2h_kernel). MT pixel tiles per CTA share each filter stage.
 template <int KC, int MT, bool STATS, bool TAIL32 = false>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
@@ -455,6 +457,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.bias = bias;
   a.stats = stats;
   a.fin = fin;
+  a.relu = g_halo_relu;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
                "conv_tc2h: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   CUtensorMap tmA, tmB, tmA32, tmB32;
@@ -513,7 +516,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
                        double* stats = nullptr, bool* stats_fused = nullptr,
                        const EpiStatsFinal* finp = nullptr, int cstride = 1,
-                       const PhasePlan* phases = nullptr, int es = 2) {
+                       const PhasePlan* phases = nullptr, int es = 2, int relu = 0) {
   // es = 4: fp32 / TF32 precision mode (fp32 activations, filters, output; SM-pair kernel only)
   // phases != nullptr: (P, Q) is the FULL output extent, tiles are planned on the (P/2, Q/2) phase grid
   EpiStatsFinal fin;
@@ -568,6 +571,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       // Cin = 64 n + 32 (the 160-channel layers): 64-channel blocks + one 32-channel tail block
       static const int mixed_env = env_int("B200_HALO_MIXED", 1);
       const bool mixed = mixed_env && !mt2 && Cin > 64 && Cin % 64 == 32;
+      g_halo_relu = relu;
       if (stats && !mt2 && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
         *stats_fused = true;
         if (mixed) return launch_conv_tc2h<64, 1, true, true>(B200_HALO_ARGS, stats, fin, st);
@@ -588,6 +592,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.num_tiles = t.tiles_w * t.tiles_h * t.tiles_n * a.n_ntiles * a.nphase;
   a.taps = taps;
   a.cstride = cstride;
+  a.relu = relu;
   B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
                "conv_tc: strided TMA box exceeds 256 elements");
   a.out = reinterpret_cast<bf16*>(out);
@@ -660,7 +665,7 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
                              const void* residual, void* y, int N, int H, int W, int C, int K,
                              int R, int S, int stride, int pad, int algo, void* ws,
                              size_t ws_bytes, b200_stream_t stream, double* stats, bool* stats_fused,
-                             const EpiStatsFinal* fin = nullptr) {
+                             const EpiStatsFinal* fin = nullptr, int relu = 0) {
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -681,13 +686,13 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
     return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, stats,
-                       stats_fused, fin);
+                       stats_fused, fin, 1, nullptr, 2, relu);
   }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
     const size_t total = (size_t)N * P * Q * K;
-    launch_k(conv_fprop_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)x, (const bf16*)w_krsc, bias, (const bf16*)residual, (bf16*)y, d);
+    launch_k(conv_fprop_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)x, (const bf16*)w_krsc, bias, (const bf16*)residual, (bf16*)y, d, relu);
     B200_LAUNCH_CHECK("conv_fprop_direct_kernel");
     return 0;
   }
@@ -695,16 +700,16 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
   // made a parity-split copy of x first: 549 TFLOP/s against cuDNN's 724 on the 160->320 layer)
   TapTable tt = fprop_taps(C, R, S, pad);
   return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, stats,
-                     stats_fused, fin, stride);
+                     stats_fused, fin, stride, nullptr, 2, relu);
 }
 
 extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float* bias,
                                  const void* residual, void* y, int N, int H, int W, int C, int K,
-                                 int R, int S, int stride, int pad, int algo, void* ws,
+                                 int R, int S, int stride, int pad, int relu, int algo, void* ws,
                                  size_t ws_bytes, b200_stream_t stream) {
   bool fused = false;
   return conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
-                           ws_bytes, stream, nullptr, &fused, nullptr);
+                           ws_bytes, stream, nullptr, &fused, nullptr, relu);
 }
 
 static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t ws_bytes, int finalize,
@@ -1227,7 +1232,7 @@ extern "C" size_t b200_conv2d_tf32_workspace_bytes(int N, int H, int W, int C, i
 
 extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const float* bias,
                                       const float* residual, float* y, int N, int H, int W, int C, int K,
-                                      int R, int S, int stride, int pad, void* ws, size_t ws_bytes,
+                                      int R, int S, int stride, int pad, int relu, void* ws, size_t ws_bytes,
                                       b200_stream_t stream) {
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop_tf32: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop_tf32: stride %d unsupported", stride);
@@ -1237,7 +1242,7 @@ extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const
   if (b200_conv2d_tf32_supported(B200_PASS_FPROP, N, H, W, C, K, R, S, stride, pad)) {
     TapTable tt = fprop_taps(C, R, S, pad);
     return run_conv_tc(x, N, H, W, C, w_krsc, K, R * S * C, tt, y, residual, bias, N, P, Q, st, nullptr, nullptr,
-                       nullptr, stride, nullptr, 4);
+                       nullptr, stride, nullptr, 4, relu);
   }
   if (tf32_use_im2col(N, H, W, C, K, R, S, stride, pad)) {
     const int kpad = im2col_kpad(R, S, C);
@@ -1253,11 +1258,11 @@ extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
     return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, nullptr, nullptr,
-                       nullptr, 1, nullptr, 4);
+                       nullptr, 1, nullptr, 4, relu);
   }
   // shapes outside the TF32 tensor path (channel counts below 32, odd tile counts): exact fp32 on the CUDA cores
   ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
-  launch_k(conv_fprop_direct_f32_kernel, ew_grid((size_t)N * P * Q * K), EW_THREADS, 0, st, x, w_krsc, bias, residual, y, d);
+  launch_k(conv_fprop_direct_f32_kernel, ew_grid((size_t)N * P * Q * K), EW_THREADS, 0, st, x, w_krsc, bias, residual, y, d, relu);
   B200_LAUNCH_CHECK("conv_fprop_direct_f32_kernel");
   return 0;
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ float dot_bf16(const bf16* __restrict__ a, const bf16
 __global__ void conv_fprop_direct_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                          const float* __restrict__ bias,
                                          const bf16* __restrict__ residual, bf16* __restrict__ y,
-                                         ConvDims d) {
+                                         ConvDims d, int relu) {
   const size_t total = (size_t)d.N * d.P * d.Q * d.K;
   const bool vec = (d.C % 8) == 0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -60,6 +60,7 @@ __global__ void conv_fprop_direct_kernel(const bf16* __restrict__ x, const bf16*
     if (bias) acc += round_bf16(bias[k]);
     float o = round_bf16(acc);
     if (residual) o = round_bf16(o + __bfloat162float(residual[idx]));
+    if (relu) o = fmaxf(o, 0.f);
     y[idx] = __float2bfloat16_rn(o);
   }
 }

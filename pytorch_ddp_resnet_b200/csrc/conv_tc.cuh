@@ -69,6 +69,7 @@ struct ConvTcArgs {
   const float* bias;
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
+  int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -331,6 +332,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             r1.to_float(rf + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+          }
+          if (args.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           Vec8 o0, o1;
           o0.from_float(f);
@@ -602,6 +607,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const float4 r = *reinterpret_cast<const float4*>(rf + 4 * q);
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
               }
+              if (args.relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
               *reinterpret_cast<float4*>(of + 4 * q) = o;
             }
           }
@@ -622,6 +630,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               rcur[ri + 1].to_float(rf + 8);
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+            }
+            if (args.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
             if (STATS) {
 #pragma unroll
@@ -691,6 +703,7 @@ struct ConvHaloArgs {
   const float* bias;
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
+  int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
 };
 
 // MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
@@ -957,6 +970,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           rcur[ri + 1].to_float(rf + 8);
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = round_bf16(f[j]) + rf[j];
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (STATS) {
 #pragma unroll

@@ -48,7 +48,7 @@ __global__ void im2col_f32_kernel(const float* __restrict__ x, float* __restrict
 // exact fp32 direct convolution for the shapes the TF32 tensor path does not take (few channels, odd tiles)
 __global__ void conv_fprop_direct_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                              const float* __restrict__ bias, const float* __restrict__ residual,
-                                             float* __restrict__ y, ConvDims d) {
+                                             float* __restrict__ y, ConvDims d, int relu) {
   const size_t total = (size_t)d.N * d.P * d.Q * d.K;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -71,7 +71,7 @@ __global__ void conv_fprop_direct_f32_kernel(const float* __restrict__ x, const 
     }
     if (bias) acc += bias[k];
     if (residual) acc += residual[idx];
-    y[idx] = acc;
+    y[idx] = relu ? fmaxf(acc, 0.f) : acc;
   }
 }
 

@@ -48,6 +48,28 @@ class precision:
         return False
 
 
+# Eval-mode batch-norm folding (utils/fold_util.py): on inside `with ops.fold_bn(True)`.
+_fold_bn = [False]
+
+
+def get_fold_bn() -> bool:
+    return _fold_bn[0]
+
+
+class fold_bn:
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = _fold_bn[0]
+        _fold_bn[0] = self.on
+        return self
+
+    def __exit__(self, *exc):
+        _fold_bn[0] = self.prev
+        return False
+
+
 def step_counter(device: torch.device) -> torch.Tensor:
     """Per-device uint64 step counter (stored as int64) that the dropout kernels fold into their seed.
     It only advances through tick(): a captured training step ticks it once per replay."""
@@ -186,7 +208,7 @@ def _out_hw(H, W, R, S, stride, pad):
 
 
 def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=None,
-               want_stats: bool = False, eps: float = 1e-5):
+               want_stats: bool = False, eps: float = 1e-5, relu: bool = False):
     """want_stats: also compute the batch-norm statistics (mean, invstd with `eps`) of the output in the conv
     kernel itself; the next bn_batch_stats(y) / bn_stats(y) picks them up."""
     _check_act(x, "conv_fprop.x")
@@ -201,6 +223,8 @@ def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=
     algo = conv_algo() if algo is None else algo
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_FPROP, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(x.device, nws) if nws else None
+    if want_stats and relu:
+        raise _lib.B200Error("conv_fprop: the epilogue ReLU belongs to evaluation (folded batch norm), not to training")
     if want_stats and K % 8 == 0 and fused_bn_stats_enabled():
         _drop_pending_stats(x.device)
         nacc = _lib.load().b200_bn_workspace_bytes(N * P * Q, K)
@@ -213,7 +237,7 @@ def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=
         _pending_stats[_accum_key(x.device)] = (y.data_ptr(), N * P * Q, K, float(eps), mean, invstd)
         return y
     _lib.call("b200_conv2d_fprop", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual),
-              y.data_ptr(), N, H, W, C, K, R, S, stride, pad, algo, _p(ws), nws, _stream())
+              y.data_ptr(), N, H, W, C, K, R, S, stride, pad, int(relu), algo, _p(ws), nws, _stream())
     return y
 
 
@@ -615,7 +639,7 @@ def conv_tf32_supported(pass_: int, N, H, W, C, K, R, S, stride, pad) -> bool:
     return bool(_lib.load().b200_conv2d_tf32_supported(pass_, N, H, W, C, K, R, S, stride, pad))
 
 
-def conv_fprop_tf32(x, w_krsc, stride: int, pad: int, bias=None, residual=None):
+def conv_fprop_tf32(x, w_krsc, stride: int, pad: int, bias=None, residual=None, relu: bool = False):
     """fp32 NHWC x, fp32 KRSC filter -> fp32 NHWC y through tcgen05 kind::tf32 MMAs."""
     _check_f32(x, "conv_fprop_tf32.x")
     _check_f32(w_krsc, "conv_fprop_tf32.w")
@@ -630,7 +654,7 @@ def conv_fprop_tf32(x, w_krsc, stride: int, pad: int, bias=None, residual=None):
     nws = _lib.load().b200_conv2d_tf32_workspace_bytes(N, H, W, C, K, R, S, stride, pad)
     ws = _workspace(x.device, nws) if nws else None
     _lib.call("b200_conv2d_fprop_tf32", x.data_ptr(), w_krsc.data_ptr(), _p(bias), _p(residual), y.data_ptr(),
-              N, H, W, C, K, R, S, stride, pad, _p(ws), nws, _stream())
+              N, H, W, C, K, R, S, stride, pad, int(relu), _p(ws), nws, _stream())
     return y
 
 

@@ -171,3 +171,64 @@ def test_evaluation_loop_uses_the_reference_precision():
     b = evaluation_loop(1, "cuda", dl, model, eval_precision="bf16")
     assert set(a) == {"loss", "top1_err", "top5_err"}
     assert abs(a["loss"] - b["loss"]) < 3e-2 and abs(a["top1_err"] - b["top1_err"]) <= 0.1
+
+
+# --------------------------------------------------------------------------------------------------
+# eval-mode batch-norm folding
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["v1_tiny", "wrn_tiny", "v2_bottleneck_tiny", "imagenet_style_tiny"])
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_bn_folding_preserves_eval_logits(case, mode):
+    """`with ops.fold_bn(True)`: conv -> BN(eval) [-> ReLU] pairs run as one conv launch; logits stay within the
+    precision mode's tolerance of the unfolded evaluation and of the reference's fp32 golden logits, and fewer
+    kernels are launched."""
+    from pytorch_ddp_resnet_b200 import _lib, ops
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    from tests.golden_util import CASES, load_case
+    c, g = CASES[case], load_case(case)
+    model = ResNet(c["spec"], c["preact"], c["use_proj"], 0.0)
+    model.load_state_dict(g["after"])
+    model = model.cuda().eval()
+    x = g["x"].cuda()
+    with torch.no_grad(), ops.precision(mode):
+        l0 = _lib.launch_count()
+        plain = model(x).float()
+        l1 = _lib.launch_count()
+        with ops.fold_bn(True):
+            folded = model(x).float()
+        l2 = _lib.launch_count()
+    tol = TF32_TOL if mode == "tf32" else 2e-2
+    ref = g["eval_logits"].cuda()
+    assert rel_l2(folded, plain) < tol and rel_l2(folded, ref) < (tol if mode == "tf32" else 3e-2)
+    assert (l2 - l1) < (l1 - l0), "folding must remove launches"
+    if mode == "tf32":
+        assert torch.equal(folded.argmax(-1), ref.argmax(-1))
+
+
+def test_bn_folding_wrn28_10_batch128():
+    from oracle import resnet_oracle as O
+    from pytorch_ddp_resnet_b200 import _lib, ops
+    from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
+    spec = "c3,160,3,1,1 r4 r4 r4 n a ap8,1,0 fc640,10"
+    init = O.init_state(spec, True, True, seed=3)
+    gen = torch.Generator().manual_seed(17)
+    for k in init:
+        if k.endswith("running_var"):
+            init[k] = torch.rand(init[k].shape, generator=gen) + 0.5
+        if k.endswith("running_mean"):
+            init[k] = torch.randn(init[k].shape, generator=gen) * 0.1
+    model = ResNet(spec, True, True, 0.3)
+    model.load_state_dict(init)
+    model = model.cuda().eval()
+    x = torch.randn(128, 3, 32, 32, generator=torch.Generator().manual_seed(9)).cuda()
+    for mode, tol in (("tf32", TF32_TOL), ("bf16", 2e-2)):
+        with torch.no_grad(), ops.precision(mode):
+            l0 = _lib.launch_count()
+            plain = model(x).float()
+            l1 = _lib.launch_count()
+            with ops.fold_bn(True):
+                folded = model(x).float()
+            l2 = _lib.launch_count()
+        print(f"WRN-28-10 eval {mode}: folded vs unfolded rel-L2 {rel_l2(folded, plain):.2e}; launches {l1 - l0} -> {l2 - l1}")
+        assert rel_l2(folded, plain) < tol
+        assert (l1 - l0) - (l2 - l1) == 12     # conv1 -> norm2 of each of the 12 blocks
