@@ -254,7 +254,7 @@ class GraphedTrainStep:
             self.plan = self.local._prep_plan
         self.reducer = FlatGradReducer(self.local, self.device, self.world, bucket_bytes, exchange,
                                        after_bucket=self._after_bucket if self.bucket_step else None) \
-            if (self.is_ddp or self.bucket_step) else None
+            if (self.is_ddp or self.bucket_step or os.environ.get("B200_FORCE_FLAT", "0") != "0") else None
         self._conv_of = {}
         if self.plan is not None:
             self._conv_of = {id(c.weight): c for c in self.plan.convs}
