@@ -19,7 +19,7 @@ for (N, H, C) in [(128, 32, 160), (128, 16, 320), (128, 8, 640)]:
         dx = ops.conv_dgrad(dy, wt, (H, H), 1, 1, algo=_lib.ALGO_TC)
         dw, _ = ops.conv_wgrad(dy, x, 3, 3, 1, 1, algo=_lib.ALGO_TC)
         mean, invstd = ops.bn_stats(x, 1e-5)
-        a = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1)
-        g = ops.bn_act_bwd(dy, a, x, mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1, addend=dy)
+        a, mk = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1, want_mask=True)
+        g = ops.bn_act_bwd(dy, None, x, mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1, addend=dy, mask=mk)
 torch.cuda.synchronize()
 print("done")
