@@ -88,7 +88,12 @@ def _worker(rank, world, port, use_graph):
         theirs = dict(twin.named_parameters()) if rank else twin.state_dict()
         for n, p in mine.items():
             q = theirs[n]
-            err = ((p.float() - q.float()).norm() / q.float().norm().clamp_min(1e-6)).item()
+            # relative to the parameter's norm, with an absolute floor of 1e-2 per element: after three steps the
+            # BN biases are ~1e-3 in size and sums of near-cancelling rank gradients, so NCCL's AVG and DDP's
+            # pre-divided SUM differ by an ulp of the gradient that a purely relative measure blows up
+            # (tools/dbg_ddp_graph.py: absolute differences <= 2e-7 after one step, 0 between two eager runs)
+            floor = 1e-2 * q.numel() ** 0.5
+            err = ((p.float() - q.float()).norm() / q.float().norm().clamp_min(floor)).item()
             assert err < 2e-3, ("graph DDP != eager DDP", n, err)
         step.close()   # graphs that hold NCCL kernels are released before the process group goes away
     else:
