@@ -1412,8 +1412,14 @@ static int bn_blocks(int64_t rows, int C, int blocks_per_sm, int unroll) {
   const int CG = C / 8;
   const int CGb = std::min(EW_THREADS, CG);
   const int RP = EW_THREADS / CGb;
-  const int64_t batches = (rows + (int64_t)RP * unroll - 1) / ((int64_t)RP * unroll);  // block-batches
+  static const int balanced = env_int("B200_BN_BALANCED", 1);
   const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  if (balanced) {
+    // a whole number of blocks per SM; the row passes are dealt out evenly (grid-stride loops / block_row_range)
+    const int64_t passes = (rows + RP - 1) / RP;
+    return (int)std::max<int64_t>(1, std::min(cap, passes));
+  }
+  const int64_t batches = (rows + (int64_t)RP * unroll - 1) / ((int64_t)RP * unroll);  // block-batches
   const int64_t per_block = (batches + cap - 1) / cap;
   return (int)std::max<int64_t>(1, (batches + per_block - 1) / per_block);
 }
@@ -1438,6 +1444,9 @@ static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t w
   a.accum = reinterpret_cast<double*>(ws);
   a.ticket = reinterpret_cast<unsigned int*>(a.accum + BN_SLOTS * bn_slot_stride(C));
   a.finalize = finalize;
+  static const int dbg = env_int("B200_DBG_BN", 0);   // DBG
+  if (dbg >= 1) a.finalize = 0;
+  if (dbg >= 2) a.accum = nullptr;
   const int CG = C / 8;
   dim3 grid(bn_blocks(rows, C, bps, 8), (CG + EW_THREADS - 1) / EW_THREADS);
   launch_k(bn_stats_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a);
@@ -1523,12 +1532,22 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
     const int64_t rows = (int64_t)N * H * W;
     static const int bps = std::max(1, env_int("B200_BN_FWD_BPS", 4));
     cudaStream_t fst = as_stream(stream);
+    const bool drop = a.drop_thr != 0;
+    const bool keepbits = drop && !relu && a.mask_out;   // no fused ReLU to read the mask off the output
     if (a.skip_mode != 0) {
       dim3 grid(bn_blocks(rows, C, std::min(bps, 3), 2), (CG + EW_THREADS - 1) / EW_THREADS);
-      launch_k(bn_act_fwd_kernel<2, 3, true>, grid, EW_THREADS, 0, fst, a);
-    } else {
+      if (drop) launch_k(bn_act_fwd_kernel<2, 3, true, 2>, grid, EW_THREADS, 0, fst, a);
+      else launch_k(bn_act_fwd_kernel<2, 3, true, 0>, grid, EW_THREADS, 0, fst, a);
+    } else if (!drop) {
       dim3 grid(bn_blocks(rows, C, bps, 4), (CG + EW_THREADS - 1) / EW_THREADS);
-      launch_k(bn_act_fwd_kernel<4, 4, false>, grid, EW_THREADS, 0, fst, a);
+      launch_k(bn_act_fwd_kernel<4, 4, false, 0>, grid, EW_THREADS, 0, fst, a);
+    } else if (keepbits) {
+      dim3 grid(bn_blocks(rows, C, std::min(bps, 3), 4), (CG + EW_THREADS - 1) / EW_THREADS);
+      launch_k(bn_act_fwd_kernel<4, 3, false, 2>, grid, EW_THREADS, 0, fst, a);
+    } else {
+      // two vectors in flight per thread: the four-vector variant spills at 64 registers once the RNG is in
+      dim3 grid(bn_blocks(rows, C, bps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
+      launch_k(bn_act_fwd_kernel<2, 4, false, 1>, grid, EW_THREADS, 0, fst, a);
     }
   }
   B200_LAUNCH_CHECK("bn_act_fwd_kernel");
@@ -1556,7 +1575,8 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, 
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
   a.seed_offset = seed_offset;
-  if (a.affine) {
+  static const int dbg_bwd = env_int("B200_DBG_BWD", 0);   // DBG
+  if (a.affine && dbg_bwd != 2) {
     B200_REQUIRE(x && dgamma && dbeta && ws, "bn_act_bwd: null pointer (affine path)");
     B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_act_bwd: workspace too small");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_act_bwd: workspace must be 8-byte aligned");
@@ -1569,12 +1589,14 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, 
     else launch_k(bn_act_bwd_reduce_kernel<false>, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, ticket);
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   }
-  {
+  if (dbg_bwd != 1) {
     static const int abps = std::max(1, env_int("B200_BN_APPLY_BPS", 3));
     const int CG = C / 8;
     dim3 grid(bn_blocks(rows, C, abps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
-    if (gate_x) launch_k(bn_act_bwd_apply_kernel<true>, grid, EW_THREADS, 0, st, a);
-    else launch_k(bn_act_bwd_apply_kernel<false>, grid, EW_THREADS, 0, st, a);
+    if (!gate_x) launch_k(bn_act_bwd_apply_kernel<false, true, true>, grid, EW_THREADS, 0, st, a);
+    else if (a.dskip) launch_k(bn_act_bwd_apply_kernel<true, true, true>, grid, EW_THREADS, 0, st, a);
+    else if (a.addend) launch_k(bn_act_bwd_apply_kernel<true, true, false>, grid, EW_THREADS, 0, st, a);
+    else launch_k(bn_act_bwd_apply_kernel<true, false, false>, grid, EW_THREADS, 0, st, a);
   }
   B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;

@@ -58,6 +58,13 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t v, float& lo, float& hi) 
   hi = __uint_as_float(v & 0xffff0000u);
 }
 
+// round 8 floats to bf16 precision in place, two at a time through one packing convert: 3 instructions per
+// pair against 4 for two round_bf16 (the element-wise BN kernels are issue-bound)
+__device__ __forceinline__ void round_bf16_pairs8(float* f) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) unpack_bf16x2(pack_bf16x2(f[j], f[j + 1]), f[j], f[j + 1]);
+}
+
 // 8 bf16 <-> 8 floats through one 16-byte vector
 struct alignas(16) Vec8 {
   uint4 raw;
@@ -166,9 +173,8 @@ struct EpiStatsFinal {
   long long rows;
 };
 
-__device__ __forceinline__ void stats_to_mean_invstd(double* accum, int C, int c, long long rows, float eps,
-                                                     float* mean, float* invstd) {
-  const double s = drain_slots(accum, C, 0, c), ss = drain_slots(accum, C, 1, c);
+__device__ __forceinline__ void sums_to_mean_invstd(double s, double ss, int c, long long rows, float eps,
+                                                    float* mean, float* invstd) {
   const double m = s / (double)rows;
   double var = ss / (double)rows - m * m;
   if (var < 0.0) var = 0.0;

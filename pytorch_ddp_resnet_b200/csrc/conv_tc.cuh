@@ -144,7 +144,8 @@ __device__ __forceinline__ void epi_stats_finalize(const EpiStatsFinal& fin, dou
   epi_bar();
   if (s_last) {
     for (int c = e; c < C; c += TC2_EPI_THREADS)
-      stats_to_mean_invstd(accum, C, c, fin.rows, fin.eps, fin.mean, fin.invstd);
+      sums_to_mean_invstd(drain_slots(accum, C, 0, c), drain_slots(accum, C, 1, c), c, fin.rows, fin.eps, fin.mean,
+                          fin.invstd);
     if (e == 0) *fin.ticket = 0u;
   }
 }

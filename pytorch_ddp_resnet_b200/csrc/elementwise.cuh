@@ -50,6 +50,7 @@ __device__ __forceinline__ void block_channel_reduce(const float* acc, float* sm
       for (int j = 0; j < 8; ++j) smem[rl * width + (a * CGb + cgl) * 8 + j] = acc[a * 8 + j];
   }
   __syncthreads();
+  if (accum == nullptr) return;   // DBG
   double* slot = accum + (size_t)(blockIdx.x % BN_SLOTS) * bn_slot_stride(C);
   for (int i = threadIdx.x; i < width; i += blockDim.x) {
     float s = 0.f;
@@ -73,6 +74,15 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
   }
   __syncthreads();
   return is_last != 0;
+}
+
+// rows [r0, r1) of block blockIdx.x: the ceil(rows / RP) row passes are dealt out as evenly as integers allow
+// (any grid size works). Round 1 rounded every block up to whole unrolled batches, which left 342 blocks for the
+// 148 SMs at 128x8x8x640: SMs with three blocks against SMs with two, in kernels that are issue-bound.
+__device__ __forceinline__ void block_row_range(int64_t rows, int RP, int64_t& r0, int64_t& r1) {
+  const int64_t passes = (rows + RP - 1) / RP;
+  r0 = passes * blockIdx.x / gridDim.x * RP;
+  r1 = min(rows, passes * (blockIdx.x + 1) / gridDim.x * RP);
 }
 
 // geometry shared by the reduction kernels: blockIdx.y selects a chunk of <=256 channel groups
@@ -122,10 +132,8 @@ __device__ __forceinline__ void bn_running_update_channel(float mean, float invs
   running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
 }
 
-// one channel: drain the accumulator slots, write mean / invstd, update the running statistics
-__device__ __forceinline__ void bn_finalize_channel(const BnStatsArgs& a, int c) {
-  const int C = a.C;
-  const double s = drain_slots(a.accum, C, 0, c), ss = drain_slots(a.accum, C, 1, c);
+// one channel: mean / invstd from its drained sums, running-statistics update
+__device__ __forceinline__ void bn_finalize_channel(const BnStatsArgs& a, int c, double s, double ss) {
   const double m = s / (double)a.rows;
   double var = ss / (double)a.rows - m * m;
   if (var < 0.0) var = 0.0;
@@ -160,10 +168,8 @@ __global__ void __launch_bounds__(EW_THREADS, 4) bn_stats_kernel(const BnStatsAr
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   if (g.active) {
     constexpr int U = 8;   // 8 independent 16-byte loads in flight per thread; rows past r1 are skipped
-    const int64_t batch = (int64_t)g.RP * U;  // whole batches per block: no ragged extra round trip
-    const int64_t rows_per_block = ((a.rows + gridDim.x - 1) / gridDim.x + batch - 1) / batch * batch;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r1 = min(a.rows, r0 + rows_per_block);
+    int64_t r0, r1;
+    block_row_range(a.rows, g.RP, r0, r1);
     const bf16* base = a.x + (size_t)(g.cg0 + g.cgl) * 8;
     for (int64_t r = r0 + g.rl; r < r1; r += U * (int64_t)g.RP) {
       Vec8 v[U];
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(EW_THREADS, 4) bn_stats_kernel(const BnStatsAr
   }
   block_channel_reduce<2>(acc, red_smem, g.cgl, g.rl, g.CGb, g.RP, g.active, a.accum, C, g.cg0 * 8);
   if (!a.finalize || !last_block_done(a.ticket)) return;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) bn_finalize_channel(a, c);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    bn_finalize_channel(a, c, drain_slots(a.accum, C, 0, c), drain_slots(a.accum, C, 1, c));
   if (threadIdx.x == 0) {
     *a.ticket = 0u;
     if (a.num_batches_tracked) *a.num_batches_tracked += 1;
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4) bn_stats_kernel(const BnStatsAr
 // sums accumulated by a conv epilogue (or an accumulate-only pass) -> mean / invstd / running statistics
 __global__ void bn_stats_finalize_kernel(const BnStatsArgs a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < a.C) bn_finalize_channel(a, c);
+  if (c < a.C) bn_finalize_channel(a, c, drain_slots(a.accum, a.C, 0, c), drain_slots(a.accum, a.C, 1, c));
   if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
 }
 
@@ -231,15 +238,52 @@ struct BnActFwdArgs {
   uint8_t* mask_out;
 };
 
+// the running-statistics update of 8 channels, kept OUT of line: inlined, its fp64 arithmetic cost the hot
+// loop of bn_act_fwd_kernel<4, 4, false> four spilled registers at its 64-register cap (16.3 -> 19.5 us at
+// 128x32x32x160)
+__device__ __noinline__ void bn_act_fwd_running_update(const float* mean, const float* invstd, float eps,
+                                                       float momentum, int64_t rows, float* running_mean,
+                                                       float* running_var, int64_t* num_batches_tracked,
+                                                       int cgi) {
+  for (int j = 0; j < 8; ++j) {
+    const int c = cgi * 8 + j;
+    bn_running_update_channel(mean[c], invstd[c], eps, momentum, rows, running_mean, running_var, c);
+  }
+  if (cgi == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+
 // Thread mapping of the element-wise BN kernels: a thread owns ONE 8-channel group for the whole
 // kernel (per-channel coefficients live in registers) and walks rows with stride RP * gridDim.x;
 // the RP x CGb threads of a block touch RP consecutive rows = one contiguous 4 KB span per pass.
-template <int U, int MINB, bool SKIP>
+// bit j of the result = half-word j of the four packed bf16x2 words is non-zero (+0 / -0 count as zero).
+// Per word: (w & 0x7fff7fff) + 0x7fff7fff carries into bit 15 / 31 exactly when the 15 magnitude bits of that
+// half are non-zero, and never across the halves.
+__device__ __forceinline__ uint32_t nonzero_bits8(const uint4& w) {
+  const uint32_t k0 = ((w.x & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+  const uint32_t k1 = ((w.y & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+  const uint32_t k2 = ((w.z & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+  const uint32_t k3 = ((w.w & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;
+  const uint32_t b = (k0 >> 15) | (k1 >> 13) | (k2 >> 11) | (k3 >> 9);   // bits 0,2,4,6 and 16,18,20,22
+  return (b | (b >> 15)) & 0xffu;
+}
+
+// DROP = false: no random numbers in the kernel at all, and the bf16 rounding of the affine result is the one
+// the final pack does (ReLU commutes with rounding); DROP = true: round, gate, scale by 1/(1-p), round again,
+// like the reference's bf16 dropout of a bf16 activation.
+// The mask byte comes from the packed OUTPUT when a ReLU is fused (y != 0 exactly where the unit was active and
+// kept): ~16 integer operations per 8 elements instead of a compare + select + merge per element and gate —
+// ncu (round 2) had this kernel at 55 % issue-slot use cold, i.e. issue-bound once the data streams warm.
+// DROP: 0 = no dropout, 1 = dropout, 2 = dropout whose keep bits ARE the mask (no fused ReLU to read it off).
+template <int U, int MINB, bool SKIP, int DROP>
 __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnActFwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
   if (!g.active) return;
   const int cgi = g.cg0 + g.cgl;
+  const int64_t rows = (int64_t)a.N * a.H * a.W;
+  if (a.running_mean && blockIdx.x == 0 && g.rl == 0)   // before anything is live in registers
+    bn_act_fwd_running_update(a.mean, a.invstd, a.eps, a.momentum, rows, a.running_mean, a.running_var,
+                              a.num_batches_tracked, cgi);
   float sc[8], sh[8];
   if (a.affine) {
 #pragma unroll
@@ -249,18 +293,11 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnAc
       sc[j] = a.gamma[c] * is;
       sh[j] = a.beta[c] - a.mean[c] * sc[j];
     }
-  }
-  const int64_t rows = (int64_t)a.N * a.H * a.W;
-  if (a.running_mean && blockIdx.x == 0 && g.rl == 0) {
+  } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cgi * 8 + j;
-      bn_running_update_channel(a.mean[c], a.invstd[c], a.eps, a.momentum, rows, a.running_mean,
-                                a.running_var, c);
-    }
-    if (cgi == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
   }
-  const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
+  const uint64_t seed = DROP ? effective_seed(a.seed, a.seed_offset) : 0;
   const bool skip_here = SKIP && (a.skip_mode == 1 || (a.skip_mode == 2 && cgi * 8 < a.skip_C));
   const int64_t stride = (int64_t)g.RP * gridDim.x;
   for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < rows; r0 += U * stride) {
@@ -291,28 +328,30 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) bn_act_fwd_kernel(const BnAc
       const size_t v = (size_t)r * g.CG + cgi;
       float f[8];
       xv[u].to_float(f);
-      if (a.affine) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = round_bf16(fmaf(f[j], sc[j], sh[j]));
-      }
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);   // sc = 1, sh = 0 without the affine part: exact
       if (SKIP && skip_here) {
         float sk[8];
         sv[SKIP ? u : 0].to_float(sk);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j] + sk[j]);
+        for (int j = 0; j < 8; ++j) f[j] = round_bf16(f[j]) + sk[j];
       }
       uint32_t bits = 0xffu;
+      if (DROP) round_bf16_pairs8(f);
       if (a.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (!(f[j] > 0.f)) bits &= ~(1u << j);
-          f[j] = fmaxf(f[j], 0.f);
-        }
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (a.drop_thr) bits &= dropout8<false>(f, seed, v, a.drop_thr, a.inv_keep);  // the pack below rounds
-      if (a.mask_out) a.mask_out[v] = (uint8_t)bits;
+      if (DROP) {   // the pack below rounds; the keep bits are dead code unless DROP == 2
+        const uint32_t keep = dropout8<false>(f, seed, v, a.drop_thr, a.inv_keep);
+        if (DROP == 2) bits = keep;
+      }
       Vec8 o;
       o.from_float(f);
+      if (a.mask_out) {
+        if (DROP != 2 && a.relu) bits = nonzero_bits8(o.raw);
+        a.mask_out[v] = (uint8_t)bits;
+      }
       stg_stream(a.y + v * 8, o.raw);
     }
   }
@@ -356,7 +395,10 @@ __device__ __forceinline__ void masked_grad_from(const BnActBwdArgs& a, uint64_t
   if (BITS) {
     if (a.drop_thr) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? round_bf16(g[j] * a.inv_keep) : 0.f;
+      for (int j = 0; j < 8; ++j) g[j] *= a.inv_keep;
+      round_bf16_pairs8(g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = ((bits >> j) & 1u) ? g[j] : 0.f;
@@ -390,10 +432,8 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
   if (g.active) {
     const int cgi = g.cg0 + g.cgl;
     constexpr int U = BITS ? 4 : 2;
-    const int64_t batch = (int64_t)g.RP * U;
-    const int64_t rows_per_block = ((a.rows + gridDim.x - 1) / gridDim.x + batch - 1) / batch * batch;
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r1 = min(a.rows, r0 + rows_per_block);
+    int64_t r0, r1;
+    block_row_range(a.rows, g.RP, r0, r1);
     for (int64_t rb = r0 + g.rl; rb < r1; rb += U * (int64_t)g.RP) {
       Vec8 dv[U], yv[BITS ? 1 : U], xv[U];
       uint32_t mb[U];
@@ -437,7 +477,10 @@ bn_act_bwd_reduce_kernel(const BnActBwdArgs a, double* __restrict__ accum, unsig
 // dx = gamma * invstd * (g - (dbeta + xhat * dgamma) / rows) [+ addend]; dskip = g.
 // Per channel this is dx = k1 * g + k2 * x + k3 with
 //   k1 = gamma*invstd, k2 = -k1*invstd*dgamma/rows, k3 = -k1*dbeta/rows - k2*mean   (registers).
-template <bool BITS>
+// ADD / DSKIP: the launch may carry an addend / a dskip output (false: the pointers are not even looked at, and
+// the addend vectors cost no registers: with them the common no-addend launch spilled nine registers per vector
+// at the 80-register cap).
+template <bool BITS, bool ADD, bool DSKIP>
 __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const BnActBwdArgs a) {
   const int C = a.C;
   ReduceGeom g(C);
@@ -455,11 +498,12 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const B
       k3[j] = -k1[j] * a.dbeta[c] * inv_rows - k2[j] * a.mean[c];
     }
   }
-  const uint64_t seed = a.drop_thr ? effective_seed(a.seed, a.seed_offset) : 0;
+  const uint64_t seed = (!BITS && a.drop_thr) ? effective_seed(a.seed, a.seed_offset) : 0;
+  const bool add = ADD && a.addend != nullptr;
   const int64_t stride = (int64_t)g.RP * gridDim.x;
   constexpr int U = 2;
   for (int64_t r0 = (int64_t)blockIdx.x * g.RP + g.rl; r0 < a.rows; r0 += U * stride) {
-    Vec8 dv[U], yv[BITS ? 1 : U], xv[U], av[U];
+    Vec8 dv[U], yv[BITS ? 1 : U], xv[U], av[ADD ? U : 1];
     uint32_t mb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -470,7 +514,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const B
         if (BITS) mb[u] = __ldg(a.mask + v);
         else if (a.relu) yv[BITS ? 0 : u].raw = ldg_stream(a.y + v * 8);
         if (a.affine) xv[u].raw = ldg_stream(a.x + v * 8);
-        if (a.addend) av[u].raw = ldg_stream(a.addend + v * 8);
+        if (add) av[ADD ? u : 0].raw = ldg_stream(a.addend + v * 8);
       }
     }
 #pragma unroll
@@ -481,23 +525,24 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_act_bwd_apply_kernel(const B
       float gr[8], d[8], xf[8];
       if (a.affine) xv[u].to_float(xf);
       masked_grad_from<BITS>(a, seed, v, dv[u], yv[BITS ? 0 : u], BITS ? mb[u] : 0u, gr);
-      if (a.dskip) {
+      if (DSKIP && a.dskip) {
         Vec8 o;
         o.from_float(gr);
         stg_stream(a.dskip + v * 8, o.raw);
       }
       if (a.affine) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = round_bf16(fmaf(k1[j], gr[j], fmaf(k2[j], xf[j], k3[j])));
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(k1[j], gr[j], fmaf(k2[j], xf[j], k3[j]));
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = gr[j];
       }
-      if (a.addend) {
+      if (add) {   // bf16 dx, then the bf16 sum: two roundings (the second one is the pack below)
         float af[8];
-        av[u].to_float(af);
+        av[ADD ? u : 0].to_float(af);
+        round_bf16_pairs8(d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = round_bf16(d[j] + af[j]);
+        for (int j = 0; j < 8; ++j) d[j] += af[j];
       }
       Vec8 o;
       o.from_float(d);
