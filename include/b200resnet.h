@@ -98,6 +98,20 @@ int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, vo
                       int W, int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
                       size_t ws_bytes, b200_stream_t stream);
 
+/* b200_conv2d_dgrad whose output dx is the dy of a batch norm + ReLU + dropout backward (the layer in FRONT of the
+ * convolution: reference resnet/architectures/residual_block.py:67-85, autograd of norm -> act -> dropout -> conv).
+ * The tcgen05 epilogue also accumulates, per channel of dx, sum(g) and sum(g * x_bn) with g = dx where the mask bit
+ * of b200_bn_act_fwd is set (scaled by 1/(1-p) and rounded to bf16 when dropout_p > 0), else 0, and the last CTA
+ * writes dbeta = sum(g), dgamma = invstd * (sum(g x) - mean * sum(g)): the whole reduction pass of b200_bn_act_bwd.
+ * x_bn: the batch norm's input [N,H,W,C] bf16; mask: uint8 [N,H,W,C/8]; stats_ws as for b200_conv2d_fprop_stats.
+ * *fused = 1: dgamma / dbeta are final, continue with b200_bn_act_bwd_apply. *fused = 0: the shape ran on a
+ * kernel without this epilogue (dx is still complete), continue with b200_bn_act_bwd. */
+int b200_conv2d_dgrad_bnbwd(const void* dy, const void* w_crsk, void* dx, int N, int H, int W, int C, int K,
+                            int R, int S, int stride, int pad, int algo, void* ws, size_t ws_bytes,
+                            const void* x_bn, const void* mask, const float* mean, const float* invstd,
+                            float dropout_p, float* dgamma, float* dbeta, void* stats_ws,
+                            size_t stats_ws_bytes, int* fused, b200_stream_t stream);
+
 /* dw[K,R,S,C] (fp32) = sum over pixels of dy (x) x. dbias (fp32 [K], may be NULL) = sum of dy. */
 int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N, int H, int W,
                       int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
@@ -201,6 +215,14 @@ int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, const void*
                     const float* gamma, float* dgamma, float* dbeta, int relu, float dropout_p,
                     uint64_t seed, const uint64_t* seed_offset, void* ws, size_t ws_bytes,
                     b200_stream_t stream);
+
+/* The second pass of b200_bn_act_bwd alone: dx (and dskip) from dy, the mask bytes, x and the per-channel sums
+ * dgamma / dbeta, which are INPUTS here (b200_conv2d_dgrad_bnbwd with *fused = 1 produced them). Needs the mask
+ * and the affine operands; no workspace, no random numbers. */
+int b200_bn_act_bwd_apply(const void* dy, const void* mask, const void* x, void* dx, void* dskip,
+                          const void* addend, int64_t rows, int C, const float* mean, const float* invstd,
+                          const float* gamma, const float* dgamma, const float* dbeta, int relu,
+                          float dropout_p, b200_stream_t stream);
 
 /* y[n,h,w,c] = x[n,2h,2w,c] (AvgPool2d(kernel 1, stride 2), residual_block.py:49,90,151,206). */
 int b200_subsample2(const void* x, void* y, int N, int H, int W, int C, b200_stream_t stream);

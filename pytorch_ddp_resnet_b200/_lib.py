@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200_bn_stats_finalize": (c_int, [c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_conv2d_dgrad": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
     "b200_conv2d_wgrad": (c_int, [_P, _P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P]),
+    "b200_conv2d_dgrad_bnbwd": (c_int, [_P, _P, _P] + _CONV_DIMS + [c_int, _P, c_size_t, _P, _P, _P, _P, c_float,
+                                        _P, _P, _P, c_size_t, _P, _P]),
     "b200_nchw_f32_to_nhwc_bf16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_bn_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "b200_bn_stats": (c_int, [_P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P,
@@ -44,6 +46,8 @@ SIGNATURES = {
                                 _P, c_int, c_int, c_int, c_float, c_uint64, _P, _P, _P, _P, c_float, _P, _P]),
     "b200_bn_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int,
                                 c_float, c_uint64, _P, _P, c_size_t, _P]),
+    "b200_bn_act_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_float,
+                                      _P]),
     "b200_subsample2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_upsample_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200_avgpool_fwd": (c_int, [_P, _P] + [c_int] * 7 + [_P]),

@@ -168,11 +168,14 @@ class _BlockFn(torch.autograd.Function):
                 dw, _ = ops.conv_wgrad(cur, a, c.kernel_size, c.kernel_size, c.stride, c.padding,
                                        out=c.grad_out)
                 dws[j] = dw
-                da = ops.conv_dgrad(cur, ctx.wt[j], (a.shape[1], a.shape[2]), c.stride, c.padding)
+                # dgrad with the reduction pass of the BN backward in its epilogue (sums is None: no such epilogue)
+                da, sums = ops.conv_dgrad_bn_bwd(cur, ctx.wt[j], (a.shape[1], a.shape[2]), c.stride, c.padding,
+                                                 x_bn=hin, mask=ctx.masks[j], mean=st["mean"], invstd=st["invstd"],
+                                                 dropout_p=p, **norms[j].grad_dst())
                 addend = dskip if (j == 0 and identity) else None
                 cur, dgs[j], dbs[j], _ = ops.bn_act_bwd(
                     da, None, hin, st["mean"], st["invstd"], st["gamma"], relu=True, dropout_p=p,
-                    seed=seeds[j], addend=addend, mask=ctx.masks[j], **norms[j].grad_dst())
+                    seed=seeds[j], addend=addend, mask=ctx.masks[j], reduced=sums, **norms[j].grad_dst())
             dx = cur
         else:
             # last BN: relu(bn(c_n) + skip)

@@ -369,7 +369,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTc
 }
 
 // SM-pair (cta_group::2) launch: tmB's box holds BN/2 filter rows
-template <int KC, bool STATS, bool TF32 = false>
+template <int KC, int STATS, bool TF32 = false>
 static int launch_conv_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvTcArgs& a,
                            cudaStream_t st) {
   const int max_dyn = STATS ? 228352 - 6144 : 228352;   // STATS: 8 KB of static shared memory for the partial sums
@@ -419,9 +419,10 @@ static bool conv_use_halo() {
 }
 
 static thread_local int g_halo_relu = 0;   // epilogue ReLU flag of the halo launch being prepared by this thread
+static thread_local EpiBnBwd g_halo_bb = {nullptr, 1.f, 0};   // STATS = 2 arguments of that launch
 
 // Halo-reuse SM-pair launch (see conv_tc2h_kernel). MT pixel tiles per CTA share each filter stage.
-template <int KC, int MT, bool STATS, bool TAIL32 = false>
+template <int KC, int MT, int STATS, bool TAIL32 = false>
 static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, const void* wmat, int Cout,
                             int wcols, const TapTable& taps, void* out, const void* residual,
                             const float* bias, int Nimg, int P, int Q, int BN, int pw, double* stats,
@@ -458,6 +459,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.stats = stats;
   a.fin = fin;
   a.relu = g_halo_relu;
+  a.bb = g_halo_bb;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
                "conv_tc2h: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   CUtensorMap tmA, tmB, tmA32, tmB32;
@@ -516,7 +518,10 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
                        const float* bias, int Nimg, int P, int Q, cudaStream_t st,
                        double* stats = nullptr, bool* stats_fused = nullptr,
                        const EpiStatsFinal* finp = nullptr, int cstride = 1,
-                       const PhasePlan* phases = nullptr, int es = 2, int relu = 0) {
+                       const PhasePlan* phases = nullptr, int es = 2, int relu = 0,
+                       const EpiBnBwd* bb = nullptr) {
+  // bb != nullptr (with stats, finp): `residual` is the BN input x of the fused BN backward whose dy this launch
+  // produces; the SM-pair kernels accumulate sum(g), sum(g * x) (STATS = 2) and *stats_fused says whether they did
   // es = 4: fp32 / TF32 precision mode (fp32 activations, filters, output; SM-pair kernel only)
   // phases != nullptr: (P, Q) is the FULL output extent, tiles are planned on the (P/2, Q/2) phase grid
   EpiStatsFinal fin;
@@ -525,6 +530,16 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   // stats != nullptr: the SM-pair kernels also accumulate the per-channel sum / sum of squares of the
   // output (fused BN statistics); *stats_fused says whether the kernel that ran did it
   if (stats_fused) *stats_fused = false;
+  // a launch that cannot carry the fused BN backward runs as the plain conv (x is NOT a residual to add)
+  auto plain_without_bb = [&]() {
+    return run_conv_tc(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, nullptr, bias, Nimg, P, Q, st, nullptr,
+                       nullptr, nullptr, cstride, phases, es, relu, nullptr);
+  };
+  if (bb) {
+    B200_REQUIRE(stats && stats_fused && finp && residual && es == 2 && !bias && !relu,
+                 "conv_tc: the fused BN backward needs x, a statistics workspace and a plain bf16 dgrad");
+    if (Cout % 16 != 0 || Cout > EPI_STATS_MAX_C) return plain_without_bb();
+  }
   int KC = pick_kc(Cin);
   if (es == 4) KC = (Cin % 32 == 0) ? 32 : (Cin % 16 == 0) ? 16 : 8;   // 128 / 64 / 32-byte rows of fp32
   int BN = pick_bn(Cout, 16, 256);
@@ -572,6 +587,14 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       static const int mixed_env = env_int("B200_HALO_MIXED", 1);
       const bool mixed = mixed_env && !mt2 && Cin > 64 && Cin % 64 == 32;
       g_halo_relu = relu;
+      if (bb) {
+        if (mt2 || (BN / 2) % 16 != 0) return plain_without_bb();
+        *stats_fused = true;
+        g_halo_bb = *bb;
+        if (mixed) return launch_conv_tc2h<64, 1, 2, true>(B200_HALO_ARGS, stats, fin, st);
+        if (KC == 64) return launch_conv_tc2h<64, 1, 2>(B200_HALO_ARGS, stats, fin, st);
+        return launch_conv_tc2h<32, 1, 2>(B200_HALO_ARGS, stats, fin, st);
+      }
       if (stats && !mt2 && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
         *stats_fused = true;
         if (mixed) return launch_conv_tc2h<64, 1, true, true>(B200_HALO_ARGS, stats, fin, st);
@@ -611,11 +634,23 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
       default: return launch_conv_tc2<8, false, true>(tmA, tmB, a, st);
     }
   }
+  if (bb && (!pair || (BN / 2) % 16 != 0)) return plain_without_bb();
   if (pair) {
     // SM pair: every CTA stages BN/2 filter rows (whole 8-row swizzle atoms, UMMA N multiple of 16)
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_nhwc(&tmA, act, Nact, Ha, Wa, Cin, KC, t.bw, t.bh, t.bn, cstride)) return rc;
     if (int rc = make_tmap_2d(&tmB, wmat, Cout, wcols, KC, BN / 2)) return rc;
+    if (bb) {
+      *stats_fused = true;
+      a.stats = stats;
+      a.fin = fin;
+      a.bb = *bb;
+      switch (KC) {
+        case 64: return launch_conv_tc2<64, 2>(tmA, tmB, a, st);
+        case 32: return launch_conv_tc2<32, 2>(tmA, tmB, a, st);
+        default: return launch_conv_tc2<16, 2>(tmA, tmB, a, st);
+      }
+    }
     if (stats && BN <= EPI_STATS_MAX_BN && Cout <= EPI_STATS_MAX_C) {
       *stats_fused = true;
       a.stats = stats;
@@ -806,9 +841,13 @@ static bool build_dgrad_phases(int R, int S, int K, int pad, PhasePlan* pp, TapT
   return true;
 }
 
-extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx,
-                                 int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
-                                 int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+// bb != nullptr: addend is the BN input x of the fused BN backward (see run_conv_tc); *fused reports whether the
+// launch accumulated (and finalized) its sums
+static int conv2d_dgrad_impl(const void* dy, const void* w_crsk, const void* addend, void* dx,
+                             int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                             int algo, void* ws, size_t ws_bytes, b200_stream_t stream,
+                             double* stats = nullptr, bool* fused = nullptr, const EpiStatsFinal* fin = nullptr,
+                             const EpiBnBwd* bb = nullptr) {
   B200_REQUIRE(dy && w_crsk && dx, "conv2d_dgrad: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -818,7 +857,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
   if (!tc) {
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
     const size_t total = (size_t)N * H * W * C;
-    launch_k(conv_dgrad_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)dy, (const bf16*)w_crsk, (const bf16*)addend, (bf16*)dx, d);
+    launch_k(conv_dgrad_direct_kernel, ew_grid(total), EW_THREADS, 0, st, (const bf16*)dy, (const bf16*)w_crsk, (const bf16*)(bb ? nullptr : addend), (bf16*)dx, d);
     B200_LAUNCH_CHECK("conv_dgrad_direct_kernel");
     return 0;
   }
@@ -832,7 +871,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
         tt.dh[i] = pad - r; tt.dw[i] = pad - s; tt.dn[i] = 0;
         tt.wcol[i] = (r * S + s) * K;
       }
-    return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dx, addend, nullptr, N, H, W, st);
+    return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, tt, dx, addend, nullptr, N, H, W, st, stats, fused, fin,
+                       1, nullptr, 2, 0, bb);
   }
   // stride 2, ONE launch: the four output parity phases (a, b) are extra tiles of the SM-pair kernel, each
   // with its own subset of the taps; the epilogue writes dx (+ addend) in place at (2h' + a, 2w' + b).
@@ -847,9 +887,10 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
                          (tp.tiles_w * tp.tiles_h * tp.tiles_n) % 2 == 0 && R * S <= TC_MAX_TAPS;
     static const int single = env_int("B200_DGRAD_S2_SINGLE", 1);
     if (all_phases && pair_ok && single)
-      return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, all, dx, addend, nullptr, N, H, W, st, nullptr,
-                         nullptr, nullptr, 1, &pp);
+      return run_conv_tc(dy, N, P, Q, K, w_crsk, C, R * S * K, all, dx, addend, nullptr, N, H, W, st, stats,
+                         fused, fin, 1, &pp, 2, 0, bb);
   }
+  if (bb) addend = nullptr;   // the per-phase fallback below does not fuse: x must not be added
   // fallback: one launch per output parity phase (a, b), into the parity-split workspace
   const size_t need = (size_t)N * H * W * C * 2;
   B200_REQUIRE(ws && ws_bytes >= need, "conv2d_dgrad: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -880,6 +921,45 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void*
   launch_k(parity_merge_add_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, st, (const bf16*)ws, (const bf16*)addend, (bf16*)dx, N, H, W, C);
   B200_LAUNCH_CHECK("parity_merge_add_kernel");
   return 0;
+}
+
+extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx,
+                                 int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
+                                 int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+  return conv2d_dgrad_impl(dy, w_crsk, addend, dx, N, H, W, C, K, R, S, stride, pad, algo, ws, ws_bytes, stream);
+}
+
+// dgrad whose output dx is the dy of a BN + ReLU + dropout backward (b200_bn_act_bwd with a mask): the epilogue
+// also accumulates sum(g) and sum(g * x_bn) per channel, g = dx masked (and scaled by 1/(1-p)), and the last CTA
+// writes dbeta / dgamma - the whole reduce pass of that backward. *fused = 1 when this happened (then call
+// b200_bn_act_bwd_apply), 0 when the shape ran on a kernel without the fused epilogue (then call b200_bn_act_bwd).
+extern "C" int b200_conv2d_dgrad_bnbwd(const void* dy, const void* w_crsk, void* dx, int N, int H, int W, int C,
+                                       int K, int R, int S, int stride, int pad, int algo, void* ws,
+                                       size_t ws_bytes, const void* x_bn, const void* mask, const float* mean,
+                                       const float* invstd, float dropout_p, float* dgamma, float* dbeta,
+                                       void* stats_ws, size_t stats_ws_bytes, int* fused, b200_stream_t stream) {
+  B200_REQUIRE(x_bn && mask && mean && invstd && dgamma && dbeta && stats_ws && fused,
+               "conv2d_dgrad_bnbwd: null pointer");
+  B200_REQUIRE(stats_ws_bytes >= b200_bn_workspace_bytes(0, C), "conv2d_dgrad_bnbwd: statistics workspace too small");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(stats_ws) & 7) == 0 && (reinterpret_cast<uintptr_t>(mask) & 1) == 0,
+               "conv2d_dgrad_bnbwd: statistics workspace must be 8-byte, the mask 2-byte aligned");
+  B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "conv2d_dgrad_bnbwd: dropout_p out of range");
+  double* accum = reinterpret_cast<double*>(stats_ws);
+  EpiStatsFinal fin;
+  memset(&fin, 0, sizeof(fin));
+  fin.ticket = reinterpret_cast<unsigned int*>(accum + BN_SLOTS * bn_slot_stride(C));
+  fin.mean = const_cast<float*>(mean); fin.invstd = const_cast<float*>(invstd);
+  fin.rows = (long long)N * H * W;
+  fin.dgamma = dgamma; fin.dbeta = dbeta;
+  EpiBnBwd bb;
+  bb.mask = reinterpret_cast<const uint8_t*>(mask);
+  bb.inv_keep = 1.f / (1.f - dropout_p);
+  bb.drop = dropout_p > 0.f ? 1 : 0;
+  bool f = false;
+  const int rc = conv2d_dgrad_impl(dy, w_crsk, x_bn, dx, N, H, W, C, K, R, S, stride, pad, algo, ws, ws_bytes,
+                                   stream, accum, &f, &fin, &bb);
+  *fused = f ? 1 : 0;
+  return rc;
 }
 
 static int wgrad_cluster_size() {
@@ -1444,9 +1524,6 @@ static int bn_sums_launch(const void* x, int64_t rows, int C, void* ws, size_t w
   a.accum = reinterpret_cast<double*>(ws);
   a.ticket = reinterpret_cast<unsigned int*>(a.accum + BN_SLOTS * bn_slot_stride(C));
   a.finalize = finalize;
-  static const int dbg = env_int("B200_DBG_BN", 0);   // DBG
-  if (dbg >= 1) a.finalize = 0;
-  if (dbg >= 2) a.accum = nullptr;
   const int CG = C / 8;
   dim3 grid(bn_blocks(rows, C, bps, 8), (CG + EW_THREADS - 1) / EW_THREADS);
   launch_k(bn_stats_kernel, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a);
@@ -1554,11 +1631,12 @@ extern "C" int b200_bn_act_fwd(const void* x, void* y, int N, int H, int W, int 
   return 0;
 }
 
-extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, const void* x, void* dx,
-                               void* dskip, const void* addend, int64_t rows, int C, const float* mean,
-                               const float* invstd, const float* gamma, float* dgamma, float* dbeta,
-                               int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
-                               void* ws, size_t ws_bytes, b200_stream_t stream) {
+// reduce = false: dgamma / dbeta already hold the sums (b200_conv2d_dgrad_bnbwd produced them), apply pass only
+static int bn_act_bwd_impl(const void* dy, const void* y, const void* mask, const void* x, void* dx,
+                           void* dskip, const void* addend, int64_t rows, int C, const float* mean,
+                           const float* invstd, const float* gamma, float* dgamma, float* dbeta,
+                           int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                           void* ws, size_t ws_bytes, b200_stream_t stream, bool reduce) {
   B200_REQUIRE(dy && dx, "bn_act_bwd: null pointer");
   B200_REQUIRE(C % 8 == 0, "bn_act_bwd: C=%d must be a multiple of 8", C);
   const bool gate_x = mask != nullptr;   // bit mask written by the forward: neither y nor the RNG is needed
@@ -1575,8 +1653,8 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, 
   a.drop_thr = drop_threshold(dropout_p);
   a.seed = seed;
   a.seed_offset = seed_offset;
-  static const int dbg_bwd = env_int("B200_DBG_BWD", 0);   // DBG
-  if (a.affine && dbg_bwd != 2) {
+  B200_REQUIRE(reduce || (a.affine && x && dgamma && dbeta), "bn_act_bwd_apply: needs the affine operands");
+  if (a.affine && reduce) {
     B200_REQUIRE(x && dgamma && dbeta && ws, "bn_act_bwd: null pointer (affine path)");
     B200_REQUIRE(ws_bytes >= b200_bn_workspace_bytes(rows, C), "bn_act_bwd: workspace too small");
     B200_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 7) == 0, "bn_act_bwd: workspace must be 8-byte aligned");
@@ -1589,7 +1667,7 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, 
     else launch_k(bn_act_bwd_reduce_kernel<false>, grid, EW_THREADS, EW_THREADS * 16 * sizeof(float), st, a, accum, ticket);
     B200_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   }
-  if (dbg_bwd != 1) {
+  {
     static const int abps = std::max(1, env_int("B200_BN_APPLY_BPS", 3));
     const int CG = C / 8;
     dim3 grid(bn_blocks(rows, C, abps, 2), (CG + EW_THREADS - 1) / EW_THREADS);
@@ -1600,6 +1678,26 @@ extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, 
   }
   B200_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return 0;
+}
+
+extern "C" int b200_bn_act_bwd(const void* dy, const void* y, const void* mask, const void* x, void* dx,
+                               void* dskip, const void* addend, int64_t rows, int C, const float* mean,
+                               const float* invstd, const float* gamma, float* dgamma, float* dbeta,
+                               int relu, float dropout_p, uint64_t seed, const uint64_t* seed_offset,
+                               void* ws, size_t ws_bytes, b200_stream_t stream) {
+  return bn_act_bwd_impl(dy, y, mask, x, dx, dskip, addend, rows, C, mean, invstd, gamma, dgamma, dbeta, relu,
+                         dropout_p, seed, seed_offset, ws, ws_bytes, stream, true);
+}
+
+// The apply pass alone: dgamma / dbeta are INPUTS (the per-channel sums b200_conv2d_dgrad_bnbwd finalized).
+extern "C" int b200_bn_act_bwd_apply(const void* dy, const void* mask, const void* x, void* dx, void* dskip,
+                                     const void* addend, int64_t rows, int C, const float* mean,
+                                     const float* invstd, const float* gamma, const float* dgamma,
+                                     const float* dbeta, int relu, float dropout_p, b200_stream_t stream) {
+  B200_REQUIRE(mask, "bn_act_bwd_apply: needs the forward's mask bytes");
+  return bn_act_bwd_impl(dy, nullptr, mask, x, dx, dskip, addend, rows, C, mean, invstd, gamma,
+                         const_cast<float*>(dgamma), const_cast<float*>(dbeta), relu, dropout_p, 0, nullptr, nullptr, 0,
+                         stream, false);
 }
 
 extern "C" int b200_subsample2(const void* x, void* y, int N, int H, int W, int C,

@@ -165,12 +165,24 @@ __device__ __forceinline__ double drain_slots(double* accum, int C, int a, int c
 // What the LAST CTA of a conv kernel with fused BN statistics does with the accumulated sums (the finalize
 // step of the batch norm that follows the conv, folded into the conv's tail): mean / invstd of `rows`
 // values per channel. mean == nullptr: leave the sums for b200_bn_stats_finalize.
+// STATS = 2 kernels (a dgrad whose output is the dy of a fused BN + ReLU + dropout backward) accumulate sum(g) and
+// sum(g * x) instead, and the last CTA turns them into dbeta / dgamma: mean / invstd are then INPUTS.
 struct EpiStatsFinal {
   unsigned int* ticket;   // zero on entry, zero again on exit
   float* mean;
   float* invstd;
   float eps;
   long long rows;
+  float* dgamma;          // STATS = 2: outputs (nullptr: leave the sums in the workspace)
+  float* dbeta;
+};
+
+// STATS = 2: what the epilogue needs of the BN + ReLU + dropout whose backward consumes this dgrad's output. x (the
+// BN input, same shape as the output) travels in the residual slot of the kernel arguments.
+struct EpiBnBwd {
+  const uint8_t* mask;    // one byte per (pixel, 8 channels): the ReLU-and-keep bits bn_act_fwd wrote
+  float inv_keep;         // 1 / (1 - p)
+  int drop;               // p > 0: g = bf16(dy * inv_keep) where kept
 };
 
 __device__ __forceinline__ void sums_to_mean_invstd(double s, double ss, int c, long long rows, float eps,

@@ -70,6 +70,7 @@ struct ConvTcArgs {
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
   int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
+  EpiBnBwd bb;                      // STATS = 2 (residual then holds the BN input x and is NOT added)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -91,12 +92,13 @@ constexpr int EPI_MAX_CHUNKS = 8;         // 16-column chunks per epilogue threa
 constexpr int EPI_STATS_MAX_BN = 256;
 constexpr int EPI_STATS_MAX_C = 1024;   // output channels a CTA can keep partial sums for (8 KB of shared memory)
 
-__device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float* s_part, int c) {
+// sv / qv: the two per-element terms of this thread's 16 columns (STATS = 1: y and y^2; STATS = 2: g and g * x)
+__device__ __forceinline__ void epi_stats_chunk2(const float* sv, const float* qv, int lane, float* s_part, int c) {
   float s[16], q[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    s[j] = fr[j];
-    q[j] = fr[j] * fr[j];
+    s[j] = sv[j];
+    q[j] = qv[j];
   }
 #pragma unroll
   for (int step = 0; step < 4; ++step) {
@@ -116,6 +118,37 @@ __device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float
   atomicAdd(&s_part[(c + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? q0 : s0);
 }
 
+__device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float* s_part, int c) {
+  float q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) q[j] = fr[j] * fr[j];
+  epi_stats_chunk2(fr, q, lane, s_part, c);
+}
+
+// STATS = 2, one 16-column chunk: f = the bf16-rounded dgrad output of this thread's row (= dy of the BN backward),
+// x = the BN input, bits = the ReLU-and-keep mask of these 16 units. g = dy (* 1/(1-p), rounded to bf16) where the
+// bit is set, else 0 - the arithmetic of masked_grad_from<true> (elementwise.cuh) - and the sums are over g, g * x.
+__device__ __forceinline__ void epi_bnbwd_chunk(const float* f, const Vec8& x0, const Vec8& x1, uint32_t bits,
+                                                bool valid, const EpiBnBwd& bb, int lane, float* s_part, int c) {
+  float g[16], q[16], xf[16];
+  x0.to_float(xf);
+  x1.to_float(xf + 8);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) g[j] = f[j];
+  if (bb.drop) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) g[j] *= bb.inv_keep;
+    round_bf16_pairs8(g);
+    round_bf16_pairs8(g + 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    g[j] = (valid && ((bits >> j) & 1u)) ? g[j] : 0.f;
+    q[j] = valid ? g[j] * xf[j] : 0.f;
+  }
+  epi_stats_chunk2(g, q, lane, s_part, c);
+}
+
 // barrier among the 256 epilogue threads of a CTA (warps 2..9), id 1 (id 0 is __syncthreads)
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -132,9 +165,10 @@ __device__ __forceinline__ void epi_stats_flush(float* s_part, double* accum, in
 
 // after the last tile of a CTA: the CTA that finishes last turns the accumulated sums into mean / invstd
 // (the finalize step of the following batch norm; saves one launch per BN layer) and clears them
+template <bool BWD>
 __device__ __forceinline__ void epi_stats_finalize(const EpiStatsFinal& fin, double* accum, int C, int e) {
   __shared__ int s_last;
-  if (fin.mean == nullptr) return;
+  if (fin.mean == nullptr || (BWD && fin.dgamma == nullptr)) return;
   // every epilogue thread of this CTA has issued its atomics (epi_stats_flush ends with a barrier)
   if (e == 0) {
     __threadfence();
@@ -143,9 +177,15 @@ __device__ __forceinline__ void epi_stats_finalize(const EpiStatsFinal& fin, dou
   }
   epi_bar();
   if (s_last) {
-    for (int c = e; c < C; c += TC2_EPI_THREADS)
-      sums_to_mean_invstd(drain_slots(accum, C, 0, c), drain_slots(accum, C, 1, c), c, fin.rows, fin.eps, fin.mean,
-                          fin.invstd);
+    for (int c = e; c < C; c += TC2_EPI_THREADS) {
+      const double s0 = drain_slots(accum, C, 0, c), s1 = drain_slots(accum, C, 1, c);
+      if (BWD) {   // dbeta = sum g, dgamma = sum g * xhat = invstd * (sum g*x - mean * sum g)
+        fin.dbeta[c] = (float)s0;
+        fin.dgamma[c] = (float)((double)fin.invstd[c] * (s1 - (double)fin.mean[c] * s0));
+      } else {
+        sums_to_mean_invstd(s0, s1, c, fin.rows, fin.eps, fin.mean, fin.invstd);
+      }
+    }
     if (e == 0) *fin.ticket = 0u;
   }
 }
@@ -378,7 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // TF32 = true: the fp32 / TF32 precision mode (the reference's evaluation path and its non-AMP training path,
 // evaluation.py:32-39, training.py:101-102): fp32 activations and filters in shared memory, kind::tf32 MMAs
 // (K = 8), fp32 output, fp32 bias / residual added without intermediate rounding. KC counts fp32 elements.
-template <int KC, bool STATS, bool TF32 = false>
+template <int KC, int STATS, bool TF32 = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvTcArgs args) {
@@ -560,12 +600,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (c_lo + 16 * i < c_hi) ldg256_stream(args.residual + off + c_lo + 16 * i, dst[2 * i].raw, dst[2 * i + 1].raw);
     };
     Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
+    // STATS = 2: the mask bytes of this thread's row slice, 16 columns per 16-bit load, prefetched like the residual
+    uint32_t mcur[STATS == 2 ? EPI_RES_VECS / 2 : 1], mnext[STATS == 2 ? EPI_RES_VECS / 2 : 1];
+    auto load_mask = [&](uint32_t* dst, size_t off) {
+      const uint16_t* mp = reinterpret_cast<const uint16_t*>(args.bb.mask) + ((off + c_lo) >> 4);
+#pragma unroll
+      for (int i = 0; i < EPI_RES_VECS / 2; ++i)
+        if (c_lo + 16 * i < c_hi) dst[STATS == 2 ? i : 0] = __ldg(mp + i);
+    };
     const bool prefetch_res = !TF32 && args.residual != nullptr;
     if (prefetch_res && pair_id < num_ptiles) {
       bool v0;
       int nt0;
       const size_t off0 = unit_row(pair_id, v0, nt0);
       if (v0) load_residual(rcur, off0);
+      if (STATS == 2 && v0) load_mask(mcur, off0);
     }
     for (int ct = pair_id; ct < num_ptiles; ct += num_pairs) {
       bool valid;
@@ -582,6 +631,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int ntn;
         const size_t offn = unit_row(ct + num_pairs, vn, ntn);
         if (vn) load_residual(rnext, offn);
+        if (STATS == 2 && vn) load_mask(mnext, offn);
       }
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u;
 #pragma unroll
@@ -625,7 +675,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
             }
-            if (rrow) {
+            if (rrow && STATS != 2) {
               float rf[16];
               rcur[ri].to_float(rf);
               rcur[ri + 1].to_float(rf + 8);
@@ -645,7 +695,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             o1.from_float(f + 8);
             stg256(orow + c, o0.raw, o1.raw);
           }
-          if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+          if (STATS == 1) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+          if (STATS == 2)
+            epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1], mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], valid,
+                            args.bb, lane, s_part + 2 * nt * args.BN, c);
         }
       }
       tc_fence_before();
@@ -654,13 +707,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (prefetch_res) {
 #pragma unroll
         for (int i = 0; i < EPI_RES_VECS; ++i) rcur[i] = rnext[i];
+        if (STATS == 2) {
+#pragma unroll
+          for (int i = 0; i < EPI_RES_VECS / 2; ++i) mcur[STATS == 2 ? i : 0] = mnext[STATS == 2 ? i : 0];
+        }
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
     if (STATS) {
       epi_stats_flush(s_part, args.stats, args.ldo, e);
-      epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+      epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }
   }
 
@@ -705,6 +762,7 @@ struct ConvHaloArgs {
   double* stats;                    // BN accumulator workspace (STATS kernels) or nullptr
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
   int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
+  EpiBnBwd bb;                      // STATS = 2 (residual then holds the BN input x and is NOT added)
 };
 
 // MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
@@ -716,7 +774,7 @@ struct ConvHaloArgs {
 // instruction rate while active) and ONE last block holds the remaining 32 channels on 64-byte rows (SWIZZLE_64B,
 // 72 %): 80 % of the MMAs run at the fast rate instead of none (round 1 ran such layers entirely on 64-byte rows).
 // The tail block has its own tensor maps (tmA32 / tmB32: 32-channel boxes) and reuses the patch / filter slots.
-template <int KC, int MT, bool STATS, bool TAIL32 = false>
+template <int KC, int MT, int STATS, bool TAIL32 = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA32, const __grid_constant__ CUtensorMap tmB32,
@@ -930,10 +988,20 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (c_lo + 16 * i < c_hi) ldg256_stream(args.residual + off + c_lo + 16 * i, dst[2 * i].raw, dst[2 * i + 1].raw);
     };
     Vec8 rcur[EPI_RES_VECS], rnext[EPI_RES_VECS];
+    // STATS = 2: the mask bytes of this thread's row slice, 16 columns per 16-bit load, prefetched like the residual
+    uint32_t mcur[STATS == 2 ? EPI_RES_VECS / 2 : 1], mnext[STATS == 2 ? EPI_RES_VECS / 2 : 1];
+    auto load_mask = [&](uint32_t* dst, size_t off) {
+      const uint16_t* mp = reinterpret_cast<const uint16_t*>(args.bb.mask) + ((off + c_lo) >> 4);
+#pragma unroll
+      for (int i = 0; i < EPI_RES_VECS / 2; ++i)
+        if (c_lo + 16 * i < c_hi) dst[STATS == 2 ? i : 0] = __ldg(mp + i);
+    };
     const bool prefetch_res = args.residual != nullptr;
     if (prefetch_res && pair_id < num_units) {
       int nt0;
-      load_residual(rcur, unit_row(pair_id, nt0));
+      const size_t off0 = unit_row(pair_id, nt0);
+      load_residual(rcur, off0);
+      if (STATS == 2) load_mask(mcur, off0);
     }
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       int nt;
@@ -946,7 +1014,9 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (prefetch_res && ct + num_pairs < num_units) {   // next unit's residual row: in flight while this one drains
         int ntn;
-        load_residual(rnext, unit_row(ct + num_pairs, ntn));
+        const size_t offn = unit_row(ct + num_pairs, ntn);
+        load_residual(rnext, offn);
+        if (STATS == 2) load_mask(mnext, offn);
       }
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * 256u + (uint32_t)(t * args.BN);
@@ -965,7 +1035,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] += round_bf16(__ldg(brow + c + j));
         }
-        if (rrow) {
+        if (rrow && STATS != 2) {
           float rf[16];
           rcur[ri].to_float(rf);
           rcur[ri + 1].to_float(rf + 8);
@@ -984,7 +1054,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o0.from_float(f);
         o1.from_float(f + 8);
         stg256(orow + c, o0.raw, o1.raw);
-        if (STATS) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+        if (STATS == 1) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+        if (STATS == 2)
+          epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1], mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], true,
+                          args.bb, lane, s_part + 2 * nt * args.BN, c);
       }
       tc_fence_before();
       __syncwarp();
@@ -992,12 +1065,16 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (prefetch_res) {
 #pragma unroll
         for (int i = 0; i < EPI_RES_VECS; ++i) rcur[i] = rnext[i];
+        if (STATS == 2) {
+#pragma unroll
+          for (int i = 0; i < EPI_RES_VECS / 2; ++i) mcur[STATS == 2 ? i : 0] = mnext[STATS == 2 ? i : 0];
+        }
       }
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
     if (STATS) {
       epi_stats_flush(s_part, args.stats, args.ldo, e);
-      epi_stats_finalize(args.fin, args.stats, args.ldo, e);
+      epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }
   }
 

@@ -7,6 +7,7 @@ Conventions (see include/b200resnet.h):
   * conv filters: bf16 [K, R, S, C] (KRSC) and bf16 [C, R, S, K] (CRSK) working copies;
   * everything per-channel / per-parameter is fp32.
 """
+import ctypes
 import os
 from typing import Optional, Tuple
 
@@ -260,6 +261,42 @@ def conv_dgrad(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, addend
     return dx
 
 
+_FUSED_BN_BWD = os.environ.get("B200_FUSED_BN_BWD", "1") != "0"   # experiment switch, read once at import
+
+
+def conv_dgrad_bn_bwd(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, *, x_bn, mask, mean, invstd,
+                      dropout_p: float = 0.0, out_dgamma=None, out_dbeta=None, algo=None):
+    """conv_dgrad whose result is the dy of the BN + ReLU + dropout backward of the layer in front of the conv
+    (x_bn: that batch norm's input, mask: the bytes its bn_act_fwd(want_mask=True) wrote). Returns (dx, sums):
+    sums = (dgamma, dbeta) when the conv epilogue reduced them (pass it to bn_act_bwd(..., reduced=sums)), None when
+    this shape has no such epilogue (then bn_act_bwd does its own reduction pass)."""
+    if not _FUSED_BN_BWD:
+        return conv_dgrad(dy, w_crsk, in_hw, stride, pad, algo=algo), None
+    _check_act(dy, "conv_dgrad_bn_bwd.dy")
+    _check_act(x_bn, "conv_dgrad_bn_bwd.x_bn")
+    N, P, Q, K = dy.shape
+    C, R, S, Kw = w_crsk.shape
+    assert Kw == K and w_crsk.dtype == torch.bfloat16 and w_crsk.is_contiguous()
+    H, W = in_hw
+    assert _out_hw(H, W, R, S, stride, pad) == (P, Q) and x_bn.shape == (N, H, W, C)
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() * 8 == x_bn.numel()
+    dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
+    dgamma = out_dgamma.view(C) if out_dgamma is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
+    dbeta = out_dbeta.view(C) if out_dbeta is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
+    algo = conv_algo() if algo is None else algo
+    nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_DGRAD, N, H, W, C, K, R, S, stride, pad, algo)
+    ws = _workspace(dy.device, nws) if nws else None
+    nst = _lib.load().b200_bn_workspace_bytes(N * H * W, C)
+    _drop_pending_stats(dy.device)
+    st = bn_accumulators(dy.device, nst)
+    fused = ctypes.c_int(0)
+    _lib.call("b200_conv2d_dgrad_bnbwd", dy.data_ptr(), w_crsk.data_ptr(), dx.data_ptr(), N, H, W, C, K, R, S, stride,
+              pad, algo, _p(ws), nws, x_bn.data_ptr(), mask.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+              float(dropout_p), dgamma.data_ptr(), dbeta.data_ptr(), st.data_ptr(), nst, ctypes.byref(fused),
+              _stream())
+    return dx, ((dgamma, dbeta) if fused.value else None)
+
+
 def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = False, algo=None,
                out=None, out_db=None):
     """Returns (dw fp32 [K,R,S,C], dbias fp32 [K] or None). `out` / `out_db`: optional preallocated
@@ -427,15 +464,26 @@ def bn_act_fwd(x, mean=None, invstd=None, gamma=None, beta=None, *, stat_is_var:
 
 def bn_act_bwd(dy, y, x, mean=None, invstd=None, gamma=None, *, relu: bool = True,
                dropout_p: float = 0.0, seed: int = 0, addend=None, want_dskip: bool = False,
-               out_dgamma=None, out_dbeta=None, mask=None):
+               out_dgamma=None, out_dbeta=None, mask=None, reduced=None):
     """Returns (dx, dgamma, dbeta, dskip). out_dgamma / out_dbeta: optional fp32 [C] destinations.
-    mask: the uint8 bit mask of bn_act_fwd(want_mask=True); with it y may be None."""
+    mask: the uint8 bit mask of bn_act_fwd(want_mask=True); with it y may be None.
+    reduced: (dgamma, dbeta) already produced by conv_dgrad_bn_bwd -> only the apply pass runs."""
     _check_act(dy, "bn_act_bwd.dy")
     C = dy.shape[-1]
     rows = dy.numel() // C
     dx = torch.empty_like(dy)
     dskip = torch.empty_like(dy) if want_dskip else None
     affine = gamma is not None
+    if reduced is not None:
+        assert affine and mask is not None and x is not None
+        dgamma, dbeta = reduced
+        if addend is not None:
+            _check_act(addend, "bn_act_bwd.addend")
+            assert addend.shape == dy.shape
+        _lib.call("b200_bn_act_bwd_apply", dy.data_ptr(), mask.data_ptr(), x.data_ptr(), dx.data_ptr(), _p(dskip),
+                  _p(addend), rows, C, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), dgamma.data_ptr(),
+                  dbeta.data_ptr(), int(relu), float(dropout_p), _stream())
+        return dx, dgamma, dbeta, dskip
     dgamma = dbeta = None
     if affine:
         dgamma = out_dgamma.view(C) if out_dgamma is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)

@@ -235,6 +235,57 @@ def test_bn_act_mask_path_equals_y_path(skip_mode):
     assert abs(keep_frac - 0.6) < 0.03
 
 
+# N, H (input side), C (input channels = BN channels), K, R, stride, pad, expect the fused epilogue
+BNBWD_SHAPES = [
+    (8, 32, 160, 160, 3, 1, 1, True),    # halo kernel, 64 + 64 + 32 channel blocks, several tiles per CTA pair
+    (16, 16, 320, 320, 3, 1, 1, True),   # halo kernel, two 160-channel output tiles
+    (32, 8, 640, 640, 3, 1, 1, True),    # 8x8 images: the SM-pair kernel without halo reuse
+    (8, 32, 160, 320, 3, 2, 1, True),    # stride-2 dgrad: four output phases in one launch
+    (8, 32, 160, 320, 1, 2, 0, None),    # 1x1 stride 2 (projection): fused or not, the result must agree
+    (4, 16, 64, 128, 3, 1, 1, True),
+    (2, 8, 24, 40, 3, 1, 1, False),      # channel counts without a tensor-core tile: plain dgrad, sums is None
+]
+
+
+@pytest.mark.parametrize("p", [0.0, 0.3])
+@pytest.mark.parametrize("shape", BNBWD_SHAPES, ids=lambda s: "x".join(map(str, s[:7])))
+def test_dgrad_with_fused_bn_backward_reduction(shape, p):
+    """conv_dgrad_bn_bwd + bn_act_bwd(reduced=...) == conv_dgrad + bn_act_bwd: the same dx bit for bit out of the conv,
+    dgamma / dbeta within fp32 summation order, and the same BN input gradient up to the bf16 rounding that the
+    slightly different sums can flip."""
+    ops, _lib = _ops()
+    N, H, C, K, R, stride, pad, expect = shape
+    P = (H + 2 * pad - R) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, H, H, C, device="cuda", generator=g).bfloat16()          # the BN input
+    dy = (torch.randn(N, P, P, K, device="cuda", generator=g) * 0.1).bfloat16()  # gradient of the conv output
+    w = (torch.randn(K, R, R, C, device="cuda", generator=g) * 0.05)
+    _, wt = ops.weight_prep(w)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.3
+    mean, invstd = ops.bn_stats(x, 1e-5)
+    _, mask = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=p, seed=5, want_mask=True)
+    addend = torch.randn(N, H, H, C, device="cuda", generator=g).bfloat16()
+
+    da0 = ops.conv_dgrad(dy, wt, (H, H), stride, pad)
+    r0 = ops.bn_act_bwd(da0, None, x, mean, invstd, gamma, relu=True, dropout_p=p, seed=5, mask=mask, addend=addend)
+    launches = _lib.launch_count()
+    da1, sums = ops.conv_dgrad_bn_bwd(dy, wt, (H, H), stride, pad, x_bn=x, mask=mask, mean=mean, invstd=invstd,
+                                      dropout_p=p)
+    r1 = ops.bn_act_bwd(da1, None, x, mean, invstd, gamma, relu=True, dropout_p=p, seed=5, mask=mask, addend=addend,
+                        reduced=sums)
+    if expect is not None:
+        assert (sums is not None) == expect
+    if sums is not None:
+        assert _lib.launch_count() - launches == 2          # the dgrad and the apply pass: no reduce kernel
+    assert torch.equal(da0, da1)
+    assert rel_l2(r1[2], r0[2]) < 1e-4 and rel_l2(r1[1], r0[1]) < 1e-4   # dbeta, dgamma
+    assert rel_l2(r1[0], r0[0]) < 2e-3
+    # the accumulators are clean again: the next statistics launch must not see leftovers
+    m2, i2 = ops.bn_stats(x, 1e-5)
+    assert torch.allclose(m2, mean, atol=1e-6) and torch.allclose(i2, invstd, rtol=1e-5)
+
+
 def test_weight_prep():
     ops, _ = _ops()
     w = torch.randn(48, 3, 3, 40, device="cuda")
