@@ -190,8 +190,17 @@ class _BlockFn(torch.autograd.Function):
                                        out=c.grad_out)
                 dws[j] = dw
                 fuse_skip = (j == 0 and identity and p == 0.0)
-                dd = ops.conv_dgrad(cur, ctx.wt[j], (d.shape[1], d.shape[2]), c.stride, c.padding,
-                                    addend=dskip if fuse_skip else None)
+                sums = None
+                if j > 0 and p == 0.0:
+                    # the dgrad output IS the dy of BN j-1's backward: its reduction pass runs in the conv epilogue
+                    st = ctx.stats[j - 1]
+                    dd, sums = ops.conv_dgrad_bn_bwd(cur, ctx.wt[j], (d.shape[1], d.shape[2]), c.stride, c.padding,
+                                                     x_bn=ctx.saved_conv[j - 1], mask=ctx.masks[j - 1],
+                                                     mean=st["mean"], invstd=st["invstd"],
+                                                     **norms[j - 1].grad_dst())
+                else:
+                    dd = ops.conv_dgrad(cur, ctx.wt[j], (d.shape[1], d.shape[2]), c.stride, c.padding,
+                                        addend=dskip if fuse_skip else None)
                 if p > 0.0:  # backward of the dropout in front of conv_j
                     dd, _, _, _ = ops.bn_act_bwd(dd, None, None, relu=False, dropout_p=p, seed=seeds[j],
                                                  addend=dskip if (j == 0 and identity) else None)
@@ -199,7 +208,7 @@ class _BlockFn(torch.autograd.Function):
                     st = ctx.stats[j - 1]
                     cur, dgs[j - 1], dbs[j - 1], _ = ops.bn_act_bwd(
                         dd, None, ctx.saved_conv[j - 1], st["mean"], st["invstd"],
-                        st["gamma"], relu=True, mask=ctx.masks[j - 1], **norms[j - 1].grad_dst())
+                        st["gamma"], relu=True, mask=ctx.masks[j - 1], reduced=sums, **norms[j - 1].grad_dst())
                 else:
                     cur = dd
             dx = cur

@@ -56,12 +56,18 @@ def main():
         wt = w.permute(3, 1, 2, 0).contiguous()
         flops = 2.0 * N * P * P * K * C * R * R
         row = {"shape": [N, H, W, C, K, R, st, pad], "gflop": flops / 1e9}
+        mean, invstd = ops.bn_stats(xs[0], 1e-5)
+        masks = [ops.bn_act_fwd(x, mean, invstd, torch.ones(C, device="cuda"), torch.zeros(C, device="cuda"),
+                                relu=True, dropout_p=0.3, seed=1, want_mask=True)[1] for x in xs]
         for name, fn in [
             ("fprop", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC)),
             ("fprop_stats", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC, want_stats=True)),
             ("fprop_res_stats", lambda i: ops.conv_fprop(xs[i % NB], w, st, pad, algo=_lib.ALGO_TC, want_stats=True,
                                                          residual=dys[(i + 1) % NB])),
             ("dgrad", lambda i: ops.conv_dgrad(dys[i % NB], wt, (H, W), st, pad, algo=_lib.ALGO_TC)),
+            ("dgrad_bnbwd", lambda i: ops.conv_dgrad_bn_bwd(dys[i % NB], wt, (H, W), st, pad, algo=_lib.ALGO_TC,
+                                                            x_bn=xs[(i + 1) % NB], mask=masks[(i + 1) % NB],
+                                                            mean=mean, invstd=invstd, dropout_p=0.3)),
             ("wgrad", lambda i: ops.conv_wgrad(dys[i % NB], xs[i % NB], R, R, st, pad, algo=_lib.ALGO_TC)),
         ]:
             ms = timeit(fn)
