@@ -956,8 +956,14 @@ extern "C" int b200_conv2d_dgrad_bnbwd(const void* dy, const void* w_crsk, void*
   bb.inv_keep = 1.f / (1.f - dropout_p);
   bb.drop = dropout_p > 0.f ? 1 : 0;
   bool f = false;
-  const int rc = conv2d_dgrad_impl(dy, w_crsk, x_bn, dx, N, H, W, C, K, R, S, stride, pad, algo, ws, ws_bytes,
-                                   stream, accum, &f, &fin, &bb);
+  // stride 2 (four output phases per launch) is left to the separate reduction pass: measured at batch 128, the
+  // fused epilogue costs 30.7 / 17.0 us on the 160<-320 @32x32 / 320<-640 @16x16 layers against 19.9 / 14.9 us
+  // for b200_bn_act_bwd's own pass, while at stride 1 it costs 18.5 / 9.0 / 10.0 us against 19.9 / 14.9 / 14.0 us
+  const bool fuse = stride == 1;
+  const int rc = fuse ? conv2d_dgrad_impl(dy, w_crsk, x_bn, dx, N, H, W, C, K, R, S, stride, pad, algo, ws, ws_bytes,
+                                          stream, accum, &f, &fin, &bb)
+                      : conv2d_dgrad_impl(dy, w_crsk, nullptr, dx, N, H, W, C, K, R, S, stride, pad, algo, ws,
+                                          ws_bytes, stream);
   *fused = f ? 1 : 0;
   return rc;
 }

@@ -93,7 +93,12 @@ constexpr int EPI_STATS_MAX_BN = 256;
 constexpr int EPI_STATS_MAX_C = 1024;   // output channels a CTA can keep partial sums for (8 KB of shared memory)
 
 // sv / qv: the two per-element terms of this thread's 16 columns (STATS = 1: y and y^2; STATS = 2: g and g * x)
-__device__ __forceinline__ void epi_stats_chunk2(const float* sv, const float* qv, int lane, float* s_part, int c) {
+// Returns this lane's share of the warp's 32-row reduction: column (lane >> 1) of the chunk, statistic (lane & 1).
+// The caller keeps one such register per chunk across ALL tiles of the CTA (epi_stats_regs_flush): round 2 first
+// added it to shared memory right here, a float atomicAdd = a compare-and-swap loop (ATOMS.CAST.SPIN) on which the
+// four warps that drain the same columns of a tile collide - the epilogue of a 160-channel tile then outlasted its
+// MMAs (6.2 us per tile at 128x32x32x160).
+__device__ __forceinline__ float epi_stats_chunk2(const float* sv, const float* qv, int lane) {
   float s[16], q[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -115,21 +120,33 @@ __device__ __forceinline__ void epi_stats_chunk2(const float* sv, const float* q
   }
   const float s0 = s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
   const float q0 = q[0] + __shfl_xor_sync(0xffffffffu, q[0], 1);
-  atomicAdd(&s_part[(c + (lane >> 1)) * 2 + (lane & 1)], (lane & 1) ? q0 : s0);
+  return (lane & 1) ? q0 : s0;
 }
 
-__device__ __forceinline__ void epi_stats_chunk(const float* fr, int lane, float* s_part, int c) {
+__device__ __forceinline__ float epi_stats_chunk(const float* fr, int lane) {
   float q[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) q[j] = fr[j] * fr[j];
-  epi_stats_chunk2(fr, q, lane, s_part, c);
+  return epi_stats_chunk2(fr, q, lane);
+}
+
+// the per-chunk registers of a warp -> the CTA's shared partial sums of channel tile `sp` (when the channel tile
+// changes between two units of the CTA, and after its last unit)
+template <int NCH>
+__device__ __forceinline__ void epi_stats_regs_flush(float* racc, float* sp, int c_lo, int c_hi, int lane) {
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int c = c_lo + 16 * ci;
+    if (c < c_hi) atomicAdd(&sp[(c + (lane >> 1)) * 2 + (lane & 1)], racc[ci]);
+    racc[ci] = 0.f;
+  }
 }
 
 // STATS = 2, one 16-column chunk: f = the bf16-rounded dgrad output of this thread's row (= dy of the BN backward),
 // x = the BN input, bits = the ReLU-and-keep mask of these 16 units. g = dy (* 1/(1-p), rounded to bf16) where the
 // bit is set, else 0 - the arithmetic of masked_grad_from<true> (elementwise.cuh) - and the sums are over g, g * x.
-__device__ __forceinline__ void epi_bnbwd_chunk(const float* f, const Vec8& x0, const Vec8& x1, uint32_t bits,
-                                                bool valid, const EpiBnBwd& bb, int lane, float* s_part, int c) {
+__device__ __forceinline__ float epi_bnbwd_chunk(const float* f, const Vec8& x0, const Vec8& x1, uint32_t bits,
+                                                 bool valid, const EpiBnBwd& bb, int lane) {
   float g[16], q[16], xf[16];
   x0.to_float(xf);
   x1.to_float(xf + 8);
@@ -146,7 +163,7 @@ __device__ __forceinline__ void epi_bnbwd_chunk(const float* f, const Vec8& x0, 
     g[j] = (valid && ((bits >> j) & 1u)) ? g[j] : 0.f;
     q[j] = valid ? g[j] * xf[j] : 0.f;
   }
-  epi_stats_chunk2(g, q, lane, s_part, c);
+  return epi_stats_chunk2(g, q, lane);
 }
 
 // barrier among the 256 epilogue threads of a CTA (warps 2..9), id 1 (id 0 is __syncthreads)
@@ -576,6 +593,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
+    float racc[STATS ? EPI_MAX_CHUNKS : 1];   // this lane's running sums, one per 16-column chunk of its warp
+#pragma unroll
+    for (int i = 0; i < (STATS ? EPI_MAX_CHUNKS : 1); ++i) racc[i] = 0.f;
+    int racc_nt = -1;                         // channel tile they belong to
     // output row of this thread in unit `ct`: element offset of its first column, validity, channel tile
     auto unit_row = [&](int ct, bool& valid, int& nt) -> size_t {
       const int phs = ct / units_per_phase;
@@ -620,6 +641,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool valid;
       int nt;
       const size_t off = unit_row(ct, valid, nt);
+      if (STATS && nt != racc_nt) {
+        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+        racc_nt = nt;
+      }
       bf16* orow = args.out + off;
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
@@ -695,10 +720,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             o1.from_float(f + 8);
             stg256(orow + c, o0.raw, o1.raw);
           }
-          if (STATS == 1) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+          if (STATS == 1) racc[STATS ? ci : 0] += epi_stats_chunk(f, lane);
           if (STATS == 2)
-            epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1], mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], valid,
-                            args.bb, lane, s_part + 2 * nt * args.BN, c);
+            racc[STATS ? ci : 0] += epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1],
+                                                    mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], valid,
+                                                    args.bb, lane);
         }
       }
       tc_fence_before();
@@ -716,6 +742,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (as == 0) aph ^= 1;
     }
     if (STATS) {
+      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
       epi_stats_flush(s_part, args.stats, args.ldo, e);
       epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }
@@ -973,6 +1000,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = e; i < 2 * EPI_STATS_MAX_C; i += TC2_EPI_THREADS) s_part[i] = 0.f;
       epi_bar();
     }
+    float racc[STATS ? EPI_MAX_CHUNKS : 1];   // this lane's running sums, one per 16-column chunk of its warp
+#pragma unroll
+    for (int i = 0; i < (STATS ? EPI_MAX_CHUNKS : 1); ++i) racc[i] = 0.f;
+    int racc_nt = -1;                         // channel tile they belong to
     auto unit_row = [&](int ct, int& nt) -> size_t {
       nt = ct % args.n_ntiles;
       const int mt = ((ct / args.n_ntiles) * 2 + crank) * MT + t;
@@ -1006,6 +1037,10 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int ct = pair_id; ct < num_units; ct += num_pairs) {
       int nt;
       const size_t off = unit_row(ct, nt);
+      if (STATS && nt != racc_nt) {
+        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+        racc_nt = nt;
+      }
       bf16* orow = args.out + off;
       const bf16* rrow = args.residual ? args.residual + off : nullptr;
       const float* brow = args.bias ? args.bias + (size_t)nt * args.BN : nullptr;
@@ -1054,10 +1089,11 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o0.from_float(f);
         o1.from_float(f + 8);
         stg256(orow + c, o0.raw, o1.raw);
-        if (STATS == 1) epi_stats_chunk(f, lane, s_part + 2 * nt * args.BN, c);
+        if (STATS == 1) racc[(STATS && ci < EPI_MAX_CHUNKS) ? ci : 0] += epi_stats_chunk(f, lane);
         if (STATS == 2)
-          epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1], mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], true,
-                          args.bb, lane, s_part + 2 * nt * args.BN, c);
+          racc[(STATS && ci < EPI_MAX_CHUNKS) ? ci : 0] +=
+              epi_bnbwd_chunk(f, rcur[ri], rcur[ri + 1], mcur[(STATS == 2 && ci < EPI_RES_VECS / 2) ? ci : 0], true,
+                              args.bb, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -1073,6 +1109,7 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
     if (STATS) {
+      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
       epi_stats_flush(s_part, args.stats, args.ldo, e);
       epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }

@@ -48,7 +48,8 @@ def timeit(fn, iters=24, warm=3):
 def main():
     res = []
     NB = 6  # rotating buffers
-    for (N, H, W, C, K, R, st, pad) in SHAPES:
+    for (N, H, W, C, K, R, st, pad) in SHAPES[:int(os.environ.get("BENCH_CONV_NSHAPES", len(SHAPES)))]:
+        N = int(os.environ.get("BENCH_CONV_N", N))
         P = (H + 2 * pad - R) // st + 1
         xs = [torch.randn(N, H, W, C, device="cuda").bfloat16() for _ in range(NB)]
         dys = [torch.randn(N, P, P, K, device="cuda").bfloat16() for _ in range(NB)]
@@ -70,6 +71,9 @@ def main():
                                                             mean=mean, invstd=invstd, dropout_p=0.3)),
             ("wgrad", lambda i: ops.conv_wgrad(dys[i % NB], xs[i % NB], R, R, st, pad, algo=_lib.ALGO_TC)),
         ]:
+            only = os.environ.get("BENCH_CONV_CASES")
+            if only and name not in only.split(","):
+                continue
             ms = timeit(fn)
             row[name + "_ms"] = ms
             row[name + "_tflops"] = flops / ms / 1e9

@@ -21,5 +21,9 @@ for (N, H, C) in [(128, 32, 160), (128, 16, 320), (128, 8, 640)]:
         mean, invstd = ops.bn_stats(x, 1e-5)
         a, mk = ops.bn_act_fwd(x, mean, invstd, gamma, beta, relu=True, dropout_p=0.3, seed=1, want_mask=True)
         g = ops.bn_act_bwd(dy, None, x, mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1, addend=dy, mask=mk)
+        # the training path: dgrad with the BN-backward reduction in its epilogue, then the apply pass alone
+        da, sums = ops.conv_dgrad_bn_bwd(dy, wt, (H, H), 1, 1, algo=_lib.ALGO_TC, x_bn=x, mask=mk, mean=mean,
+                                         invstd=invstd, dropout_p=0.3)
+        g2 = ops.bn_act_bwd(da, None, x, mean, invstd, gamma, relu=True, dropout_p=0.3, seed=1, mask=mk, reduced=sums)
 torch.cuda.synchronize()
 print("done")
