@@ -42,6 +42,14 @@ sys.path.insert(0, ROOT)
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 SGD = dict(lr=0.1, momentum=0.9, dampening=0.0, nesterov=True, weight_decay=5e-4)
+
+
+def sgd_args(cfg):
+    """The reference recipe's SGD arguments; a config may carry its own learning rate (the ImageNet-shape net
+    diverges at 0.1 on random labels in BOTH implementations: profiles/r02_imagenet_loss_trajectory.txt)."""
+    a = dict(SGD)
+    a["lr"] = cfg.get("lr", a["lr"])
+    return a
 METRIC = "train img/s WRN-28-10 CIFAR"
 
 # BASELINE.json configs (SURVEY 8d, App. A). `classes_multi`: head used when N > 1 (config 5: CIFAR-100)
@@ -60,7 +68,7 @@ CONFIGS = {
                    workload="ResNet-v2-164 preact-bottleneck CIFAR-10-shape 32x32 synthetic bf16 training, "
                             "batch 128/GPU"),
     "wrn50-imagenet": dict(spec="c3,512,7,2,3 n a mp3,2,1 b3 b4 b6 b3 ap7,1,0 fc4096,{classes}", preact=False,
-                           use_proj=True, dropout=0.0, hw=224, batch=256, classes=1000, classes_multi=1000,
+                           use_proj=True, dropout=0.0, hw=224, batch=256, classes=1000, classes_multi=1000, lr=0.005,
                            metric="train img/s WRN-50-2-like ImageNet",
                            workload="WRN-50-2-like bottleneck ImageNet-shape 224x224 synthetic bf16 training, "
                                     "batch 256/GPU (the true WRN-50-2 is not expressible in the reference's "
@@ -221,7 +229,7 @@ def reference_training_loop(cfg, device: str, steps: int, warmup: int, mode: str
     torch.manual_seed(0)
     model = RefResNet(architecture_spec=cfg["spec"], preact=cfg["preact"], use_proj=cfg["use_proj"],
                       dropout_prob=cfg["dropout"]).to(device)
-    opt = ref_get_optimizer("SGD", model, dict(SGD))
+    opt = ref_get_optimizer("SGD", model, sgd_args(cfg))
     g = torch.Generator().manual_seed(1234)
     n = warmup + steps
     B, hw = cfg["batch"], cfg["hw"]
@@ -266,10 +274,10 @@ def port_steps(cfg, batch: int, steps: int, warmup: int):
     x = torch.randn(batch, 3, cfg["hw"], cfg["hw"], generator=g)
     y = torch.randint(0, cfg["classes"], (batch,), generator=g)
     for _ in range(warmup):
-        O.train_step(state, bufs, x, y, cfg["spec"], cfg["preact"], cfg["use_proj"], cfg["dropout"], dict(SGD))
+        O.train_step(state, bufs, x, y, cfg["spec"], cfg["preact"], cfg["use_proj"], cfg["dropout"], sgd_args(cfg))
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step(state, bufs, x, y, cfg["spec"], cfg["preact"], cfg["use_proj"], cfg["dropout"], dict(SGD))
+        O.train_step(state, bufs, x, y, cfg["spec"], cfg["preact"], cfg["use_proj"], cfg["dropout"], sgd_args(cfg))
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt / steps
 
@@ -388,7 +396,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = ResNet(cfg["spec"], cfg["preact"], cfg["use_proj"], cfg["dropout"]).to(device).train()
     classifier = wrap_ddp(model, device) if world > 1 else model
-    opt = get_optimizer("SGD", classifier, dict(SGD))
+    opt = get_optimizer("SGD", classifier, sgd_args(cfg))
 
     gen = torch.Generator().manual_seed(1234 + rank)
     nbuf = 4
