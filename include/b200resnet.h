@@ -33,6 +33,14 @@ typedef void* b200_stream_t; /* a cudaStream_t */
 
 /* conv algorithm selector */
 enum { B200_ALGO_AUTO = 0, B200_ALGO_DIRECT = 1, B200_ALGO_TC = 2 };
+/* Flag, or-ed into any `algo` argument: DETERMINISTIC reductions (the analogue of cuDNN's deterministic algorithms
+ * behind torch.use_deterministic_algorithms). b200_conv2d_wgrad then reduces its pixel-range splits (and the
+ * blocks of the bias gradient) in a fixed order from partials kept in the workspace - pass the flag to
+ * b200_conv2d_workspace_bytes too - instead of fp32 atomics in completion order; the conv epilogues with fused
+ * statistics (b200_conv2d_fprop_stats, b200_conv2d_dgrad_bnbwd) sum their per-warp partials in a fixed order
+ * instead of shared-memory atomics. Same inputs => bit-identical outputs, run after run. Without the flag the
+ * last bits of weight gradients and batch statistics depend on the order in which CTAs finish. */
+enum { B200_ALGO_DETERMINISTIC = 0x100 };
 /* which conv pass a workspace query refers to */
 enum { B200_PASS_FPROP = 0, B200_PASS_DGRAD = 1, B200_PASS_WGRAD = 2 };
 /* skip-connection addressing for the fused BN kernels */
@@ -112,7 +120,9 @@ int b200_conv2d_dgrad_bnbwd(const void* dy, const void* w_crsk, void* dx, int N,
                             float dropout_p, float* dgamma, float* dbeta, void* stats_ws,
                             size_t stats_ws_bytes, int* fused, b200_stream_t stream);
 
-/* dw[K,R,S,C] (fp32) = sum over pixels of dy (x) x. dbias (fp32 [K], may be NULL) = sum of dy. */
+/* dw[K,R,S,C] (fp32) = sum over pixels of dy (x) x. dbias (fp32 [K], may be NULL) = sum of dy.
+ * dw may point into a flat gradient bucket. With B200_ALGO_DETERMINISTIC in `algo` the reduction over pixel
+ * ranges is ordered (16-byte aligned workspace of b200_conv2d_workspace_bytes(B200_PASS_WGRAD, ..., same algo)). */
 int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N, int H, int W,
                       int C, int K, int R, int S, int stride, int pad, int algo, void* ws,
                       size_t ws_bytes, b200_stream_t stream);

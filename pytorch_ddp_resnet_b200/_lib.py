@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200resnet.so")
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_TC = 0, 1, 2
+ALGO_DETERMINISTIC = 0x100   # flag or-ed into an algo: fixed-order reductions (B200_ALGO_DETERMINISTIC)
 PASS_FPROP, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 SKIP_NONE, SKIP_SAME, SKIP_SUBSAMPLE_PAD = 0, 1, 2
 

@@ -78,6 +78,27 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// Deterministic mode (B200_ALGO_DETERMINISTIC or-ed into an entry point's `algo`): every cross-CTA / cross-warp fp32
+// reduction runs in a fixed order - wgrad pixel-range splits and bias-gradient blocks store partials that
+// wgrad_reduce_splits_kernel sums in order (instead of fp32 atomics into a zeroed gradient), the conv epilogues
+// flush their statistics partials quadrant by quadrant (instead of shared-memory float atomics). The fp64
+// accumulator atomics of the BN sums stay: their addends are fp32 values, whose fp64 sum is exact - hence
+// independent of the order - unless the partials of one channel span more than ~2^21 in magnitude.
+// The flag of the call being prepared by this thread (entry points set it, launch helpers read it):
+static thread_local int g_det = 0;
+static inline void take_det_flag(int& algo) {
+  g_det = (algo & B200_ALGO_DETERMINISTIC) ? 1 : 0;
+  algo &= ~B200_ALGO_DETERMINISTIC;
+}
+
+// partial-gradient workspace of a deterministic wgrad (dry: only report the split count the launch would use)
+struct WgradDet {
+  float* part;
+  size_t bytes;
+  bool dry;
+  int splits;
+};
+
 // Per-device caches (one process may drive several GPUs): SM count, and "max dynamic shared memory
 // already raised for this kernel on this device".
 constexpr int MAX_DEVICES = 64;
@@ -311,8 +332,18 @@ static bool use_im2col(int algo, int pass, int N, int H, int W, int C, int K, in
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static void wgrad_det_regions(int N, int H, int W, int C, int K, int R, int S, int stride, int pad, int algo,
+                              size_t* dbias_bytes, size_t* part_bytes);
+
 extern "C" size_t b200_conv2d_workspace_bytes(int pass, int N, int H, int W, int C, int K, int R,
                                               int S, int stride, int pad, int algo) {
+  if (pass == B200_PASS_WGRAD && (algo & B200_ALGO_DETERMINISTIC)) {   // + the ordered-reduction partials
+    algo &= ~B200_ALGO_DETERMINISTIC;
+    size_t dbias_bytes = 0, part_bytes = 0;
+    wgrad_det_regions(N, H, W, C, K, R, S, stride, pad, algo, &dbias_bytes, &part_bytes);
+    return b200_conv2d_workspace_bytes(pass, N, H, W, C, K, R, S, stride, pad, algo) + dbias_bytes + part_bytes;
+  }
+  algo &= ~B200_ALGO_DETERMINISTIC;
   if (algo == B200_ALGO_DIRECT) return 0;
   if (use_im2col(algo, pass, N, H, W, C, K, R, S, stride, pad)) {
     const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -460,6 +491,7 @@ static int launch_conv_tc2h(const void* act, int Nact, int Ha, int Wa, int Cin, 
   a.fin = fin;
   a.relu = g_halo_relu;
   a.bb = g_halo_bb;
+  a.det = g_det;
   B200_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0,
                "conv_tc2h: output and residual must be 32-byte aligned (256-bit epilogue accesses)");
   CUtensorMap tmA, tmB, tmA32, tmB32;
@@ -616,6 +648,7 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
   a.taps = taps;
   a.cstride = cstride;
   a.relu = relu;
+  a.det = g_det;
   B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
                "conv_tc: strided TMA box exceeds 256 elements");
   a.out = reinterpret_cast<bf16*>(out);
@@ -742,6 +775,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w_krsc, const float*
                                  const void* residual, void* y, int N, int H, int W, int C, int K,
                                  int R, int S, int stride, int pad, int relu, int algo, void* ws,
                                  size_t ws_bytes, b200_stream_t stream) {
+  take_det_flag(algo);
   bool fused = false;
   return conv2d_fprop_impl(x, w_krsc, bias, residual, y, N, H, W, C, K, R, S, stride, pad, algo, ws,
                            ws_bytes, stream, nullptr, &fused, nullptr, relu);
@@ -756,6 +790,7 @@ extern "C" int b200_conv2d_fprop_stats(const void* x, const void* w_krsc, const 
                                        int R, int S, int stride, int pad, int algo, void* ws,
                                        size_t ws_bytes, void* stats_ws, size_t stats_ws_bytes, float eps,
                                        float* mean, float* invstd, b200_stream_t stream) {
+  take_det_flag(algo);
   B200_REQUIRE(stats_ws && K % 8 == 0, "conv2d_fprop_stats: needs a statistics workspace and K %% 8 == 0");
   B200_REQUIRE(stats_ws_bytes >= b200_bn_workspace_bytes(0, K), "conv2d_fprop_stats: statistics workspace too small");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(stats_ws) & 7) == 0, "conv2d_fprop_stats: statistics workspace must be 8-byte aligned");
@@ -926,6 +961,7 @@ static int conv2d_dgrad_impl(const void* dy, const void* w_crsk, const void* add
 extern "C" int b200_conv2d_dgrad(const void* dy, const void* w_crsk, const void* addend, void* dx,
                                  int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
                                  int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+  take_det_flag(algo);
   return conv2d_dgrad_impl(dy, w_crsk, addend, dx, N, H, W, C, K, R, S, stride, pad, algo, ws, ws_bytes, stream);
 }
 
@@ -938,6 +974,7 @@ extern "C" int b200_conv2d_dgrad_bnbwd(const void* dy, const void* w_crsk, void*
                                        size_t ws_bytes, const void* x_bn, const void* mask, const float* mean,
                                        const float* invstd, float dropout_p, float* dgamma, float* dbeta,
                                        void* stats_ws, size_t stats_ws_bytes, int* fused, b200_stream_t stream) {
+  take_det_flag(algo);
   B200_REQUIRE(x_bn && mask && mean && invstd && dgamma && dbeta && stats_ws && fused,
                "conv2d_dgrad_bnbwd: null pointer");
   B200_REQUIRE(stats_ws_bytes >= b200_bn_workspace_bytes(0, C), "conv2d_dgrad_bnbwd: statistics workspace too small");
@@ -1054,6 +1091,37 @@ static int pick_wgrad_splits(int cols, int num_ptiles, int fixed_units) {
   return (num_ptiles + per - 1) / per;
 }
 
+// deterministic mode: sum `splits` partials of n floats (stride apart) in order into out
+static int wgrad_reduce_splits(const float* part, float* out, size_t n, size_t stride, int splits, cudaStream_t st) {
+  const size_t work = (n % 4 == 0) ? n / 4 : n;
+  launch_k(wgrad_reduce_splits_kernel, ew_grid(work), EW_THREADS, 0, st, part, out, n, stride, splits);
+  B200_LAUNCH_CHECK("wgrad_reduce_splits_kernel");
+  return 0;
+}
+
+// Where the pixel-range splits of a wgrad launch put their results: into the partial buffer of a deterministic
+// call (returns 1), else into dw, zeroed here when there is more than one split (returns 0); < 0: error.
+static int wgrad_split_target(const WgradDet* det, int splits, size_t n, float* dw, cudaStream_t st, float** part,
+                              size_t* part_stride) {
+  *part = nullptr;
+  *part_stride = 0;
+  if (splits <= 1) return 0;
+  if (det && det->part) {
+    if (det->bytes < (size_t)splits * n * 4) {
+      fail(1, "conv2d_wgrad: deterministic workspace too small (%zu < %zu bytes)", det->bytes, (size_t)splits * n * 4);
+      return -2;
+    }
+    *part = det->part;
+    *part_stride = n;
+    return 1;
+  }
+  if (cudaMemsetAsync(dw, 0, n * 4, st) != cudaSuccess) {
+    fail(2, "cudaMemsetAsync(dw) failed");
+    return -2;
+  }
+  return 0;
+}
+
 static bool wgrad_use_halo() {
   // B200_WGRAD_HALO=0 falls back to the one-window-per-slab kernel
   static const int v = env_int("B200_WGRAD_HALO", 1);
@@ -1063,7 +1131,7 @@ static bool wgrad_use_halo() {
 // Halo-reuse SM-pair wgrad (3x3, stride 1, pad 1): see wgrad_tc2h_kernel. Returns -1 when the shape is
 // not covered (the caller then uses the general kernel).
 static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, int C, int K,
-                          const TapTable& taps, float* dw, cudaStream_t st) {
+                          const TapTable& taps, float* dw, cudaStream_t st, WgradDet* det) {
   if (taps.n != 9 || C % 32 != 0 || K % 32 != 0 || Q % 8 != 0) return -1;
   for (int t = 0; t < 9; ++t)
     if (taps.dh[t] != t / 3 - 1 || taps.dw[t] != t % 3 - 1 || taps.dn[t] != 0) return -1;
@@ -1096,8 +1164,9 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   a.splits = pick_wgrad_splits(a.ncols * a.n_ntiles, a.num_ptiles, 5);
   for (int t = 0; t < 9; ++t) a.wcol[t] = taps.wcol[t];
   a.dw = dw;
+  if (det && det->dry) { det->splits = a.splits; return 0; }
   B200_CUDA(ensure_max_smem<wgrad_tc2h_kernel>(max_dyn));
-  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
+  if (wgrad_split_target(det, a.splits, (size_t)K * a.ktot, dw, st, &a.part, &a.part_stride) < 0) return 1;
   CUtensorMap tmX, tmDy;
   if (int rc = make_tmap_nhwc(&tmX, act, N, P, Q, C, 32, pw, bh, bn)) return rc;
   if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, 32, 8, bh, bn)) return rc;
@@ -1117,6 +1186,7 @@ static int run_wgrad_tc2h(const void* act, const void* dy, int N, int P, int Q, 
   cfg.numAttrs = 1;
   B200_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc2h_kernel, tmX, tmDy, a));
   B200_LAUNCH_CHECK("wgrad_tc2h_kernel");
+  if (a.part) return wgrad_reduce_splits(a.part, dw, (size_t)K * a.ktot, a.part_stride, a.splits, st);
   return 0;
 }
 
@@ -1160,9 +1230,10 @@ static int run_wgrad_tc_tf32(const void* act, int Nact, int Ha, int Wa, int C, c
 }
 
 static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const void* dy, int N, int P,
-                        int Q, int K, const TapTable& taps, float* dw, cudaStream_t st, int cstride = 1) {
+                        int Q, int K, const TapTable& taps, float* dw, cudaStream_t st, int cstride = 1,
+                        WgradDet* det = nullptr) {
   if (wgrad_use_halo() && Nact == N && Ha == P && Wa == Q && cstride == 1) {
-    const int rc = run_wgrad_tc2h(act, dy, N, P, Q, C, K, taps, dw, st);
+    const int rc = run_wgrad_tc2h(act, dy, N, P, Q, C, K, taps, dw, st, det);
     if (rc >= 0) return rc;
   }
   // slab width: 32 channels (64-byte TMA rows, SWIZZLE_64B) or 16; 64-channel slabs (SWIZZLE_128B, with
@@ -1210,35 +1281,105 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
   a.cstride = cstride;
   B200_REQUIRE(cstride == 1 || (t.bw * cstride <= 256 && t.bh * cstride <= 256),
                "wgrad_tc: strided TMA box exceeds 256 elements");
-  if (a.splits > 1) B200_CUDA(cudaMemsetAsync(dw, 0, (size_t)K * a.ktot * 4, st));
+  if (det && det->dry) { det->splits = a.splits; return 0; }
+  if (wgrad_split_target(det, a.splits, (size_t)K * a.ktot, dw, st, &a.part, &a.part_stride) < 0) return 1;
   CUtensorMap tmX, tmDy;
   if (int rc = make_tmap_nhwc(&tmX, act, Nact, Ha, Wa, C, SL, t.bw, t.bh, t.bn, cstride)) return rc;
   if (int rc = make_tmap_nhwc(&tmDy, dy, N, P, Q, K, SL, t.bw, t.bh, t.bn)) return rc;
-  if (SL == 64) return launch_wgrad_tc_cs<64>(cs, mt, tmX, tmDy, a, st);
-  if (SL == 32) return launch_wgrad_tc_cs<32>(cs, mt, tmX, tmDy, a, st);
-  return launch_wgrad_tc_cs<16>(cs, mt, tmX, tmDy, a, st);
+  int rc;
+  if (SL == 64) rc = launch_wgrad_tc_cs<64>(cs, mt, tmX, tmDy, a, st);
+  else if (SL == 32) rc = launch_wgrad_tc_cs<32>(cs, mt, tmX, tmDy, a, st);
+  else rc = launch_wgrad_tc_cs<16>(cs, mt, tmX, tmDy, a, st);
+  if (rc) return rc;
+  if (a.part) return wgrad_reduce_splits(a.part, dw, (size_t)K * a.ktot, a.part_stride, a.splits, st);
+  return 0;
+}
+
+// geometry shared by b200_conv2d_wgrad and its workspace query
+static int dbias_pix_per_block(size_t npix) {
+  // ONE block per SM: every block ends with K same-address atomics, which serialise (592 blocks took 46 us
+  // for the 42 MB stem gradient in round 2's launch list, most of it in the atomics)
+  return (int)std::max<size_t>(64, (npix + (size_t)num_sms() - 1) / (size_t)num_sms());
+}
+static int direct_wgrad_chunks(int total, size_t npix, int* pix_per_chunk) {
+  const int bx = (total + 255) / 256;
+  int chunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_sms() * 8 / bx + 1, npix / 64 + 1));
+  const int ppc = (int)((npix + chunks - 1) / chunks);
+  *pix_per_chunk = ppc;
+  return (int)((npix + ppc - 1) / ppc);
+}
+
+// Deterministic wgrad workspace = [im2col region][bias-gradient partials][filter-gradient partials]; sizes of the
+// last two (0 when the launch would not split)
+static void wgrad_det_regions(int N, int H, int W, int C, int K, int R, int S, int stride, int pad, int algo,
+                              size_t* dbias_bytes, size_t* part_bytes) {
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  const size_t npix = (size_t)N * P * Q;
+  const int ppc = dbias_pix_per_block(npix);
+  *dbias_bytes = align_up((npix + ppc - 1) / ppc * (size_t)K * 4, 1024);
+  *part_bytes = 0;
+  WgradDet dry = {nullptr, 0, true, 1};
+  const bool tc = use_tc(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);
+  if (!tc && use_im2col(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad)) {
+    const int kpad = im2col_kpad(R, S, C);
+    TapTable tt;
+    memset(&tt, 0, sizeof(tt));
+    tt.n = 1;
+    if (run_wgrad_tc(nullptr, N, P, Q, kpad, nullptr, N, P, Q, K, tt, nullptr, nullptr, 1, &dry) == 0 && dry.splits > 1)
+      *part_bytes = align_up((size_t)dry.splits * K * kpad * 4, 1024);
+    return;
+  }
+  if (!tc) {
+    int ppc_w;
+    const int chunks = direct_wgrad_chunks(K * R * S * C, npix, &ppc_w);
+    if (chunks > 1) *part_bytes = align_up((size_t)chunks * K * R * S * C * 4, 1024);
+    return;
+  }
+  TapTable tt = fprop_taps(C, R, S, pad);
+  if (run_wgrad_tc(nullptr, N, H, W, C, nullptr, N, P, Q, K, tt, nullptr, nullptr, stride, &dry) == 0 && dry.splits > 1)
+    *part_bytes = align_up((size_t)dry.splits * K * R * S * C * 4, 1024);
 }
 
 extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, float* dbias, int N,
                                  int H, int W, int C, int K, int R, int S, int stride, int pad,
                                  int algo, void* ws, size_t ws_bytes, b200_stream_t stream) {
+  take_det_flag(algo);
+  const bool det = g_det != 0;
   B200_REQUIRE(dy && x && dw_krsc, "conv2d_wgrad: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   cudaStream_t st = as_stream(stream);
   const size_t npix = (size_t)N * P * Q;
-  if (dbias) {
-    B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
-    B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
-    // ONE block per SM: every block ends with K same-address atomics, which serialise (592 blocks took 46 us
-    // for the 42 MB stem gradient in round 2's launch list, most of it in the atomics)
-    const int ppc = (int)std::max<size_t>(64, (npix + (size_t)num_sms() - 1) / (size_t)num_sms());
-    launch_k(conv_dbias_kernel, dim3((unsigned)((npix + ppc - 1) / ppc), 1), 256, 0, st, (const bf16*)dy, dbias,
-                                                                                    npix, K, ppc);
-    B200_LAUNCH_CHECK("conv_dbias_kernel");
-  }
   const bool tc = use_tc(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);
-  if (!tc && use_im2col(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad)) {
+  const bool im2col = !tc && use_im2col(algo, B200_PASS_WGRAD, N, H, W, C, K, R, S, stride, pad);
+  // workspace regions (see wgrad_det_regions)
+  size_t base_bytes = 0, dbias_bytes = 0, part_bytes = 0;
+  if (im2col) {
+    const int kpad = im2col_kpad(R, S, C);
+    base_bytes = align_up((size_t)N * P * Q * kpad * 2, 1024) + align_up((size_t)K * kpad * 4, 1024);
+  }
+  if (det) {
+    wgrad_det_regions(N, H, W, C, K, R, S, stride, pad, algo, &dbias_bytes, &part_bytes);
+    B200_REQUIRE(ws && ws_bytes >= base_bytes + dbias_bytes + part_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+                 "conv2d_wgrad: deterministic mode needs a 16-byte aligned workspace of %zu bytes (got %zu)",
+                 base_bytes + dbias_bytes + part_bytes, ws_bytes);
+  }
+  float* dbias_part = det ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + base_bytes) : nullptr;
+  WgradDet wd = {det ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + base_bytes + dbias_bytes) : nullptr,
+                 part_bytes, false, 1};
+  if (dbias) {
+    B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
+    const int ppc = dbias_pix_per_block(npix);
+    const unsigned nblk = (unsigned)((npix + ppc - 1) / ppc);
+    const bool part = det && nblk > 1;
+    if (!part) B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
+    launch_k(conv_dbias_kernel, dim3(nblk, 1), 256, 0, st, (const bf16*)dy, dbias, npix, K, ppc,
+             part ? dbias_part : (float*)nullptr);
+    B200_LAUNCH_CHECK("conv_dbias_kernel");
+    if (part)
+      if (int rc = wgrad_reduce_splits(dbias_part, dbias, (size_t)K, (size_t)K, (int)nblk, st)) return rc;
+  }
+  if (im2col) {
     const int kpad = im2col_kpad(R, S, C);
     const size_t col_bytes = align_up((size_t)N * P * Q * kpad * 2, 1024);
     B200_REQUIRE(ws && ws_bytes >= col_bytes + (size_t)K * kpad * 4, "conv2d_wgrad: workspace too small");
@@ -1249,7 +1390,7 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
-    if (int rc = run_wgrad_tc(col, N, P, Q, kpad, dy, N, P, Q, K, tt, dwpad, st)) return rc;
+    if (int rc = run_wgrad_tc(col, N, P, Q, kpad, dy, N, P, Q, K, tt, dwpad, st, 1, det ? &wd : nullptr)) return rc;
     launch_k(repitch_rows_kernel<float>, ew_grid((size_t)K * R * S * C), EW_THREADS, 0, st, dwpad, dw_krsc, K, kpad, R * S * C);
     B200_LAUNCH_CHECK("repitch_rows_kernel");
     return 0;
@@ -1259,17 +1400,18 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
     ConvDims d{N, H, W, C, K, R, S, stride, pad, P, Q};
     const int total = K * R * S * C;
     const int bx = (total + 255) / 256;
-    int chunks = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_sms() * 8 / bx + 1, npix / 64 + 1));
-    const int ppc = (int)((npix + chunks - 1) / chunks);
-    chunks = (int)((npix + ppc - 1) / ppc);
-    if (chunks > 1) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)total * 4, st));
+    int ppc;
+    const int chunks = direct_wgrad_chunks(total, npix, &ppc);
+    const bool part = det && chunks > 1;
+    if (chunks > 1 && !part) B200_CUDA(cudaMemsetAsync(dw_krsc, 0, (size_t)total * 4, st));
     launch_k(conv_wgrad_direct_kernel, dim3(bx, chunks), 256, 0, st, (const bf16*)dy, (const bf16*)x,
-                                                               dw_krsc, d, ppc);
+                                                               dw_krsc, d, ppc, part ? wd.part : (float*)nullptr);
     B200_LAUNCH_CHECK("conv_wgrad_direct_kernel");
+    if (part) return wgrad_reduce_splits(wd.part, dw_krsc, (size_t)total, (size_t)total, chunks, st);
     return 0;
   }
   TapTable tt = fprop_taps(C, R, S, pad);   // stride 2: strided TMA windows of x, no parity-split copy
-  return run_wgrad_tc(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, st, stride);
+  return run_wgrad_tc(x, N, H, W, C, dy, N, P, Q, K, tt, dw_krsc, st, stride, det ? &wd : nullptr);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1320,6 +1462,7 @@ extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const
                                       const float* residual, float* y, int N, int H, int W, int C, int K,
                                       int R, int S, int stride, int pad, int relu, void* ws, size_t ws_bytes,
                                       b200_stream_t stream) {
+  g_det = 0;
   B200_REQUIRE(x && w_krsc && y, "conv2d_fprop_tf32: null pointer");
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fprop_tf32: stride %d unsupported", stride);
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -1356,6 +1499,7 @@ extern "C" int b200_conv2d_fprop_tf32(const float* x, const float* w_krsc, const
 extern "C" int b200_conv2d_dgrad_tf32(const float* dy, const float* w_crsk, const float* addend, float* dx,
                                       int N, int H, int W, int C, int K, int R, int S, int stride, int pad,
                                       b200_stream_t stream) {
+  g_det = 0;
   B200_REQUIRE(dy && w_crsk && dx, "conv2d_dgrad_tf32: null pointer");
   B200_REQUIRE(b200_conv2d_tf32_supported(B200_PASS_DGRAD, N, H, W, C, K, R, S, stride, pad),
                "conv2d_dgrad_tf32: shape not supported in the fp32/TF32 mode");
@@ -1444,8 +1588,8 @@ extern "C" int b200_ce_topk_f32(const float* logits, const int64_t* labels, floa
                                 b200_stream_t stream) {
   B200_REQUIRE(logits && labels && out, "ce_topk_f32: null pointer");
   cudaStream_t st = as_stream(stream);
-  B200_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
-  launch_k(ce_topk_f32_kernel, (unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, st, logits, labels, out, B, O);
+  B200_REQUIRE(B > 0 && O > 0, "ce_topk_f32: empty batch");
+  launch_k(ce_topk_f32_kernel, 1, CE_WARPS * 32, 0, st, logits, labels, out, B, O);
   B200_LAUNCH_CHECK("ce_topk_f32_kernel");
   return 0;
 }
@@ -1804,9 +1948,8 @@ extern "C" int b200_ce_topk(const void* logits, const int64_t* labels, float* ou
                             const float* grad_scale, int B, int O, b200_stream_t stream) {
   B200_REQUIRE(logits && labels, "ce_topk: null pointer");
   cudaStream_t st = as_stream(stream);
-  if (out) B200_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(float), st));
-  const size_t threads = (size_t)B * 32;
-  launch_k(ce_topk_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
+  B200_REQUIRE(B > 0 && O > 0, "ce_topk: empty batch");
+  launch_k(ce_topk_kernel, 1, CE_WARPS * 32, 0, st, (const bf16*)logits, labels, out, (bf16*)dlogits, grad_scale, B, O);
   B200_LAUNCH_CHECK("ce_topk_kernel");
   return 0;
 }

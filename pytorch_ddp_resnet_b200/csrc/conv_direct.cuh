@@ -100,9 +100,11 @@ __global__ void conv_dgrad_direct_kernel(const bf16* __restrict__ dy, const bf16
   }
 }
 
-// thread per filter element (k, r, s, c) and pixel chunk (blockIdx.y); fp32 atomics across chunks
+// thread per filter element (k, r, s, c) and pixel chunk (blockIdx.y); fp32 atomics across chunks, or (part !=
+// nullptr, deterministic mode) one partial per chunk at part + chunk * total for wgrad_reduce_splits_kernel
 __global__ void conv_wgrad_direct_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                         float* __restrict__ dw, ConvDims d, int pix_per_chunk) {
+                                         float* __restrict__ dw, ConvDims d, int pix_per_chunk,
+                                         float* __restrict__ part) {
   const int total = d.K * d.R * d.S * d.C;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -125,13 +127,15 @@ __global__ void conv_wgrad_direct_kernel(const bf16* __restrict__ dy, const bf16
                __bfloat162float(x[(((size_t)n * d.H + ih) * d.W + iw) * d.C + c]), acc);
   }
   if (gridDim.y == 1) dw[idx] = acc;
+  else if (part) part[(size_t)blockIdx.y * total + idx] = acc;
   else atomicAdd(dw + idx, acc);
 }
 
 // dbias[k] = sum over pixels of dy[pix][k]: block = (8-channel group lanes) x (pixel lanes) over a chunk
-// of pixels, 16-byte loads, shared-memory reduction over the pixel lanes, one atomic per channel per block
+// of pixels, 16-byte loads, shared-memory reduction over the pixel lanes, one atomic per channel per block (or,
+// part != nullptr: the block's sums stored at part + blockIdx.x * K for wgrad_reduce_splits_kernel)
 __global__ void conv_dbias_kernel(const bf16* __restrict__ dy, float* __restrict__ dbias,
-                                  size_t npix, int K, int pix_per_chunk) {
+                                  size_t npix, int K, int pix_per_chunk, float* __restrict__ part) {
   __shared__ float red[256 * 8];
   const int CG = K / 8;
   const int CGb = min(256, CG);
@@ -168,7 +172,8 @@ __global__ void conv_dbias_kernel(const bf16* __restrict__ dy, float* __restrict
       for (int j = 0; j < 8; ++j) {
         float s = 0.f;
         for (int r = 0; r < RP; ++r) s += red[(r * CGb + cg) * 8 + j];
-        atomicAdd(dbias + cgi * 8 + j, s);
+        if (part) part[(size_t)blockIdx.x * K + cgi * 8 + j] = s;
+        else atomicAdd(dbias + cgi * 8 + j, s);
       }
     }
     __syncthreads();

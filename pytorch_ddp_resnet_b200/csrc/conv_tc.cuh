@@ -71,6 +71,7 @@ struct ConvTcArgs {
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
   int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
   EpiBnBwd bb;                      // STATS = 2 (residual then holds the BN input x and is NOT added)
+  int det;                          // deterministic mode: fixed-order reduction of the epilogue statistics
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -132,8 +133,27 @@ __device__ __forceinline__ float epi_stats_chunk(const float* fr, int lane) {
 
 // the per-chunk registers of a warp -> the CTA's shared partial sums of channel tile `sp` (when the channel tile
 // changes between two units of the CTA, and after its last unit)
+// det_wq < 0: shared-memory float atomics (the four warps of the four TMEM lane quadrants add to the same slots in
+// whatever order they arrive). det_wq = the warp's quadrant (deterministic mode): the quadrants take turns,
+// separated by barriers among the epilogue warps, so every slot is summed in the fixed order 0, 1, 2, 3 (the two
+// warps of one quadrant own disjoint columns). Every epilogue warp of the CTA makes this call for the same units.
 template <int NCH>
-__device__ __forceinline__ void epi_stats_regs_flush(float* racc, float* sp, int c_lo, int c_hi, int lane) {
+__device__ __forceinline__ void epi_stats_regs_flush(float* racc, float* sp, int c_lo, int c_hi, int lane,
+                                                     int det_wq) {
+  if (det_wq >= 0) {
+    for (int turn = 0; turn < 4; ++turn) {
+      if (det_wq == turn) {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = c_lo + 16 * ci;
+          if (c < c_hi) sp[(c + (lane >> 1)) * 2 + (lane & 1)] += racc[ci];
+          racc[ci] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    return;
+  }
 #pragma unroll
   for (int ci = 0; ci < NCH; ++ci) {
     const int c = c_lo + 16 * ci;
@@ -642,7 +662,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int nt;
       const size_t off = unit_row(ct, valid, nt);
       if (STATS && nt != racc_nt) {
-        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane,
+                                                              args.det ? wq : -1);
         racc_nt = nt;
       }
       bf16* orow = args.out + off;
@@ -742,7 +763,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (as == 0) aph ^= 1;
     }
     if (STATS) {
-      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane,
+                                                              args.det ? wq : -1);
       epi_stats_flush(s_part, args.stats, args.ldo, e);
       epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }
@@ -790,6 +812,7 @@ struct ConvHaloArgs {
   EpiStatsFinal fin;                // in-kernel finalize of the statistics (fin.mean == nullptr: off)
   int relu;                         // epilogue ReLU after bias / residual (eval with batch norm folded into the conv)
   EpiBnBwd bb;                      // STATS = 2 (residual then holds the BN input x and is NOT added)
+  int det;                          // deterministic mode: fixed-order reduction of the epilogue statistics
 };
 
 // MT = pixel tiles per CTA that share every filter stage (MT accumulators of BN columns in TMEM, single-
@@ -1038,7 +1061,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int nt;
       const size_t off = unit_row(ct, nt);
       if (STATS && nt != racc_nt) {
-        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+        if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane,
+                                                              args.det ? wq : -1);
         racc_nt = nt;
       }
       bf16* orow = args.out + off;
@@ -1109,7 +1133,8 @@ conv_tc2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++as == NBUF) { as = 0; aph ^= 1; }
     }
     if (STATS) {
-      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane);
+      if (racc_nt >= 0) epi_stats_regs_flush<EPI_MAX_CHUNKS>(racc, s_part + 2 * racc_nt * args.BN, c_lo, c_hi, lane,
+                                                              args.det ? wq : -1);
       epi_stats_flush(s_part, args.stats, args.ldo, e);
       epi_stats_finalize<STATS == 2>(args.fin, args.stats, args.ldo, e);
     }
@@ -1150,6 +1175,11 @@ struct WgradTcArgs {
   uint32_t slab_bytes;   // rows per stage * SL * 2 (also the descriptor's leading byte offset)
   TapTable taps;
   float* dw;
+  // deterministic mode: pixel-range split y stores its partial filter gradient at part + y * part_stride (plain
+  // stores, same indexing as dw) and wgrad_reduce_splits_kernel sums the splits in a fixed order; nullptr: the
+  // splits add into a zeroed dw with fp32 atomics, in whatever order they finish
+  float* part;
+  size_t part_stride;
 };
 
 template <int SL, int ES = 2>
@@ -1342,14 +1372,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         valid = c < args.cin;  // rows of a partial last slab
         col = args.taps.wcol[t] + c;
       }
-      float* drow = args.dw + (size_t)nt * args.BN * args.ktot + col;
+      float* drow = (args.part ? args.part + (size_t)blockIdx.y * args.part_stride : args.dw) +
+                    (size_t)nt * args.BN * args.ktot + col;
       const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)j * 256u;
       for (int c = 0; c < args.BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
         if (valid) {
-          if (args.splits == 1) {
+          if (args.splits == 1 || args.part) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj)
               drow[(size_t)(c + jj) * args.ktot] = __uint_as_float(v[jj]);
@@ -1404,6 +1435,8 @@ struct WgradHaloArgs {
   uint32_t box_bytes, slab_bytes, stage_bytes;
   int wcol[TC_MAX_TAPS];
   float* dw;
+  float* part;             // deterministic mode, see WgradTcArgs
+  size_t part_stride;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -1541,13 +1574,14 @@ wgrad_tc2h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
-        float* drow = args.dw + (size_t)nt * args.BN * args.ktot + args.wcol[r * 3 + j] + c;
+        float* drow = (args.part ? args.part + (size_t)blockIdx.y * args.part_stride : args.dw) +
+                      (size_t)nt * args.BN * args.ktot + args.wcol[r * 3 + j] + c;
         const uint32_t t_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(j * args.BN);
         for (int cc = 0; cc < args.BN; cc += 16) {
           uint32_t v[16];
           tmem_ld16(t_addr + cc, v);
           tmem_ld_wait();
-          if (args.splits == 1) {
+          if (args.splits == 1 || args.part) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj)
               drow[(size_t)(cc + jj) * args.ktot] = __uint_as_float(v[jj]);
@@ -1570,6 +1604,28 @@ wgrad_tc2h_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_dealloc_2sm(tmem_base, 512);
   }
 }
-
+// Deterministic mode: out[i] = part[0][i] + part[1][i] + ... + part[splits-1][i], in that order (fp32), for the
+// filter-gradient partials of the pixel-range splits and for the per-block partials of the bias gradient.
+__global__ void wgrad_reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n,
+                                           size_t stride, int splits) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  if ((n & 3) == 0 && (stride & 3) == 0 && (((uintptr_t)part | (uintptr_t)out) & 15) == 0) {
+    for (size_t i = i0; i < (n >> 2); i += step) {
+      float4 a = __ldcs(reinterpret_cast<const float4*>(part) + i);
+      for (int s = 1; s < splits; ++s) {
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(part + (size_t)s * stride) + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      reinterpret_cast<float4*>(out)[i] = a;
+    }
+  } else {
+    for (size_t i = i0; i < n; i += step) {
+      float a = part[i];
+      for (int s = 1; s < splits; ++s) a += part[(size_t)s * stride + i];
+      out[i] = a;
+    }
+  }
+}
 
 }  // namespace b200

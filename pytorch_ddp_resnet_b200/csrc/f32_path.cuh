@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "conv_direct.cuh"
+#include "head_sgd.cuh"
 
 namespace b200 {
 
@@ -191,35 +192,36 @@ __global__ void linear_fwd_f32_kernel(const float* __restrict__ x, const float* 
   if (lane == 0) y[(size_t)b * O + o] = acc + (bias ? bias[o] : 0.f);
 }
 
-// mean cross entropy, top-1 / top-5 error of fp32 logits (out zeroed before the launch); one warp per sample
-__global__ void ce_topk_f32_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
-                                   float* __restrict__ out, int B, int O) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// mean cross entropy, top-1 / top-5 error of fp32 logits; one block, fixed-order sums (see ce_topk_kernel)
+__global__ void __launch_bounds__(CE_WARPS * 32)
+ce_topk_f32_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                   float* __restrict__ out, int B, int O) {
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (b >= B) return;
-  const float* row = logits + (size_t)b * O;
-  const int label = (int)labels[b];
-  float mx = -INFINITY;
-  for (int o = lane; o < O; o += 32) mx = fmaxf(mx, row[o]);
+  float loss = 0.f, e1 = 0.f, e5 = 0.f;
+  for (int b = warp; b < B; b += CE_WARPS) {
+    const float* row = logits + (size_t)b * O;
+    const int label = (int)labels[b];
+    float mx = -INFINITY;
+    for (int o = lane; o < O; o += 32) mx = fmaxf(mx, row[o]);
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  float se = 0.f;
-  for (int o = lane; o < O; o += 32) se += expf(row[o] - mx);
-  se = warp_sum(se);
-  const float lse = mx + logf(se);
-  const float zl = row[label];
-  float rank = 0.f;
-  for (int o = lane; o < O; o += 32) {
-    const float z = row[o];
-    rank += (z > zl || (z == zl && o < label)) ? 1.f : 0.f;
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    float se = 0.f;
+    for (int o = lane; o < O; o += 32) se += expf(row[o] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    const float zl = row[label];
+    float rank = 0.f;
+    for (int o = lane; o < O; o += 32) {
+      const float z = row[o];
+      rank += (z > zl || (z == zl && o < label)) ? 1.f : 0.f;
+    }
+    rank = warp_sum(rank);
+    loss += lse - zl;
+    e1 += rank >= 1.f ? 1.f : 0.f;
+    e5 += rank >= 5.f ? 1.f : 0.f;
   }
-  rank = warp_sum(rank);
-  if (lane == 0) {
-    const float invB = 1.f / (float)B;
-    atomicAdd(out + 0, (lse - zl) * invB);
-    atomicAdd(out + 1, (rank >= 1.f ? 1.f : 0.f) * invB);
-    atomicAdd(out + 2, (rank >= 5.f ? 1.f : 0.f) * invB);
-  }
+  ce_block_sum3(loss, e1, e5, out, B);
 }
 
 }  // namespace b200

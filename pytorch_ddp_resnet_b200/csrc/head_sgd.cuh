@@ -54,47 +54,64 @@ __global__ void linear_bwd_dw_kernel(const bf16* __restrict__ dy, const bf16* __
   if (i == 0 && db) db[o] = accb;
 }
 
-// One warp per sample. out[0] += loss_b / B, out[1] += (label not top-1) / B, out[2] += (not in
-// top-5) / B (out must be zeroed before the launch). dlogits = (softmax - onehot) * scale / B.
-__global__ void ce_topk_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels,
-                               float* __restrict__ out, bf16* __restrict__ dlogits,
-                               const float* __restrict__ grad_scale, int B, int O) {
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// ONE block of CE_WARPS warps; warp w handles samples w, w + CE_WARPS, ... out[0] = mean loss, out[1] = fraction of
+// labels that are not the top-1, out[2] = not in the top-5 (written, not accumulated: no zeroing needed).
+// dlogits = (softmax - onehot) * scale / B. The sums run in a FIXED order (per warp over its samples, then over the
+// warps): the reported loss is bit-reproducible (round 1 added one atomic per sample, in completion order).
+constexpr int CE_WARPS = 32;
+
+__device__ __forceinline__ void ce_block_sum3(float loss, float e1, float e5, float* __restrict__ out, int B) {
+  __shared__ float s_acc[CE_WARPS][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_acc[warp][0] = loss; s_acc[warp][1] = e1; s_acc[warp][2] = e5; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < CE_WARPS; ++w) t += s_acc[w][threadIdx.x];
+    out[threadIdx.x] = t / (float)B;
+  }
+}
+
+__global__ void __launch_bounds__(CE_WARPS * 32)
+ce_topk_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ labels,
+               float* __restrict__ out, bf16* __restrict__ dlogits,
+               const float* __restrict__ grad_scale, int B, int O) {
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (b >= B) return;
-  const bf16* row = logits + (size_t)b * O;
-  const int label = (int)labels[b];
-  float mx = -INFINITY;
-  for (int o = lane; o < O; o += 32) mx = fmaxf(mx, __bfloat162float(row[o]));
+  float loss = 0.f, e1 = 0.f, e5 = 0.f;
+  for (int b = warp; b < B; b += CE_WARPS) {
+    const bf16* row = logits + (size_t)b * O;
+    const int label = (int)labels[b];
+    float mx = -INFINITY;
+    for (int o = lane; o < O; o += 32) mx = fmaxf(mx, __bfloat162float(row[o]));
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  float se = 0.f;
-  for (int o = lane; o < O; o += 32) se += __expf(__bfloat162float(row[o]) - mx);
-  se = warp_sum(se);
-  const float lse = mx + __logf(se);
-  const float zl = __bfloat162float(row[label]);
-  if (out) {
-    // rank of the label: logits strictly larger, ties broken towards the lower index
-    float rank = 0.f;
-    for (int o = lane; o < O; o += 32) {
-      const float z = __bfloat162float(row[o]);
-      rank += (z > zl || (z == zl && o < label)) ? 1.f : 0.f;
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    float se = 0.f;
+    for (int o = lane; o < O; o += 32) se += __expf(__bfloat162float(row[o]) - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    const float zl = __bfloat162float(row[label]);
+    if (out) {
+      // rank of the label: logits strictly larger, ties broken towards the lower index
+      float rank = 0.f;
+      for (int o = lane; o < O; o += 32) {
+        const float z = __bfloat162float(row[o]);
+        rank += (z > zl || (z == zl && o < label)) ? 1.f : 0.f;
+      }
+      rank = warp_sum(rank);
+      loss += lse - zl;
+      e1 += rank >= 1.f ? 1.f : 0.f;
+      e5 += rank >= 5.f ? 1.f : 0.f;
     }
-    rank = warp_sum(rank);
-    if (lane == 0) {
-      const float invB = 1.f / (float)B;
-      atomicAdd(out + 0, (lse - zl) * invB);
-      atomicAdd(out + 1, (rank >= 1.f ? 1.f : 0.f) * invB);
-      atomicAdd(out + 2, (rank >= 5.f ? 1.f : 0.f) * invB);
-    }
-  }
-  if (dlogits) {
-    const float sc = (grad_scale ? *grad_scale : 1.f) / (float)B;
-    for (int o = lane; o < O; o += 32) {
-      const float p = __expf(__bfloat162float(row[o]) - lse);
-      dlogits[(size_t)b * O + o] = __float2bfloat16_rn((p - (o == label ? 1.f : 0.f)) * sc);
+    if (dlogits) {
+      const float sc = (grad_scale ? *grad_scale : 1.f) / (float)B;
+      for (int o = lane; o < O; o += 32) {
+        const float p = __expf(__bfloat162float(row[o]) - lse);
+        dlogits[(size_t)b * O + o] = __float2bfloat16_rn((p - (o == label ? 1.f : 0.f)) * sc);
+      }
     }
   }
+  if (out) ce_block_sum3(loss, e1, e5, out, B);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -49,6 +49,39 @@ class precision:
         return False
 
 
+# Deterministic mode: every cross-CTA / cross-warp fp32 reduction of the step runs in a fixed order (wgrad
+# pixel-range splits and bias-gradient blocks from ordered partials instead of fp32 atomics, conv-epilogue
+# statistics quadrant by quadrant), so a step is bit-reproducible run after run and graph replay == eager.
+# On inside `with ops.deterministic():`, after torch.use_deterministic_algorithms(True), or with
+# B200_DETERMINISTIC=1 in the environment (read once at import). Off by default, like cuDNN in the reference.
+_deterministic = [os.environ.get("B200_DETERMINISTIC", "0") not in ("", "0")]
+
+
+def is_deterministic() -> bool:
+    return _deterministic[0] or torch.are_deterministic_algorithms_enabled()
+
+
+class deterministic:
+    """with ops.deterministic(): loss.backward()   # bit-reproducible weight gradients and batch statistics"""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = bool(enabled)
+
+    def __enter__(self):
+        self.prev = _deterministic[0]
+        _deterministic[0] = self.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _deterministic[0] = self.prev
+        return False
+
+
+def _algo_flags(algo: Optional[int]) -> int:
+    algo = conv_algo() if algo is None else algo
+    return (algo | _lib.ALGO_DETERMINISTIC) if is_deterministic() else algo
+
+
 # Eval-mode batch-norm folding (utils/fold_util.py): on inside `with ops.fold_bn(True)`.
 _fold_bn = [False]
 
@@ -221,7 +254,7 @@ def conv_fprop(x, w_krsc, stride: int, pad: int, bias=None, residual=None, algo=
     if residual is not None:
         _check_act(residual, "conv_fprop.residual")
         assert residual.shape == y.shape
-    algo = conv_algo() if algo is None else algo
+    algo = _algo_flags(algo)
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_FPROP, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(x.device, nws) if nws else None
     if want_stats and relu:
@@ -253,7 +286,7 @@ def conv_dgrad(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int, addend
     if addend is not None:
         _check_act(addend, "conv_dgrad.addend")
         assert addend.shape == dx.shape
-    algo = conv_algo() if algo is None else algo
+    algo = _algo_flags(algo)
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_DGRAD, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(dy.device, nws) if nws else None
     _lib.call("b200_conv2d_dgrad", dy.data_ptr(), w_crsk.data_ptr(), _p(addend), dx.data_ptr(),
@@ -283,7 +316,7 @@ def conv_dgrad_bn_bwd(dy, w_crsk, in_hw: Tuple[int, int], stride: int, pad: int,
     dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
     dgamma = out_dgamma.view(C) if out_dgamma is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
     dbeta = out_dbeta.view(C) if out_dbeta is not None else torch.empty((C,), dtype=torch.float32, device=dy.device)
-    algo = conv_algo() if algo is None else algo
+    algo = _algo_flags(algo)
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_DGRAD, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(dy.device, nws) if nws else None
     nst = _lib.load().b200_bn_workspace_bytes(N * H * W, C)
@@ -327,7 +360,7 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
     db = None
     if want_dbias:
         db = out_db.view(K) if out_db is not None else torch.empty((K,), dtype=torch.float32, device=x.device)
-    algo = conv_algo() if algo is None else algo
+    algo = _algo_flags(algo)
     nws = _lib.load().b200_conv2d_workspace_bytes(_lib.PASS_WGRAD, N, H, W, C, K, R, S, stride, pad, algo)
     ws = _workspace(x.device, nws) if nws else None
     _lib.call("b200_conv2d_wgrad", dy.data_ptr(), x.data_ptr(), dw.data_ptr(), _p(db),

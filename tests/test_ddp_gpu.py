@@ -59,6 +59,12 @@ def _worker(rank, world, port, use_graph):
     for n, gmean in means.items():
         err = ((ddp_grads[n] - gmean).norm() / gmean.norm().clamp_min(1e-2 * scale)).item()
         assert err < 1e-3, (n, err)
+    # deterministic mode (B200_DETERMINISTIC=1): every local gradient is bit-reproducible, and with two ranks both
+    # averaging orders (stock DDP: g/2 + g'/2, here: (g + g')/2) are exact in fp32 => the DDP gradient EQUALS the mean
+    from pytorch_ddp_resnet_b200 import ops
+    if ops.is_deterministic() and world == 2:
+        for n, gmean in means.items():
+            assert torch.equal(ddp_grads[n], gmean), ("deterministic DDP gradient != mean of rank gradients", n)
 
     # (2) replicas stay identical through optimizer steps (eager or whole-step CUDA graph)
     opt = get_optimizer("SGD", ddp, dict(SGD))

@@ -36,6 +36,21 @@ def test_library_exports_every_header_symbol():
     assert lib.b200_conv2d_workspace_bytes(0, 128, 32, 32, 160, 320, 3, 3, 2, 1, 0) == 0
     assert lib.b200_conv2d_workspace_bytes(1, 128, 32, 32, 160, 320, 3, 3, 2, 1, 0) == 128 * 32 * 32 * 160 * 2
     assert lib.b200_bn_workspace_bytes(131072, 160) > 0
+    # deterministic mode: the flag value matches the header, and the wgrad workspace grows by the ordered-reduction
+    # partials (whole filter-gradient copies, one per pixel-range split, + the bias-gradient partials)
+    flag = int(re.search(r"B200_ALGO_DETERMINISTIC\s*=\s*(0x[0-9a-fA-F]+|\d+)", header).group(1), 0)
+    assert flag == _lib.ALGO_DETERMINISTIC
+    for (N, H, C, K, R, st, pad) in [(128, 32, 160, 160, 3, 1, 1), (128, 8, 640, 640, 3, 1, 1),
+                                     (128, 32, 160, 320, 3, 2, 1), (128, 32, 3, 160, 3, 1, 1)]:
+        base = lib.b200_conv2d_workspace_bytes(2, N, H, H, C, K, R, R, st, pad, 0)
+        det = lib.b200_conv2d_workspace_bytes(2, N, H, H, C, K, R, R, st, pad, flag)
+        extra = det - base
+        assert extra > 0 and extra < (1 << 30), (N, H, C, K, extra)
+        if C >= 16:
+            dw_bytes = K * R * R * C * 4
+            assert extra >= 2 * dw_bytes and (extra - extra % dw_bytes) // dw_bytes <= 64, (extra, dw_bytes)
+    # the flag changes nothing for fprop / dgrad workspaces
+    assert lib.b200_conv2d_workspace_bytes(1, 128, 32, 32, 160, 320, 3, 3, 2, 1, flag) == 128 * 32 * 32 * 160 * 2
 
 
 def test_no_cpu_fallback():
