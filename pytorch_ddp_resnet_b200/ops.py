@@ -345,9 +345,18 @@ def conv_wgrad(dy, x, R: int, S: int, stride: int, pad: int, want_dbias: bool = 
                 res = conv_wgrad(dy, x, R, S, stride, pad, want_dbias, algo, out, out_db)
         finally:
             _overlap["on"] = True
-        # (a bias gradient that lives in a caller-owned slot is NOT kept: an extra reference would make autograd
-        #  clone it instead of adopting the slot as .grad)
-        _overlap["keep"][x.device.index].append((dy, x, res[0], None if out_db is not None else res[1]))
+        # The outputs are kept alive through their STORAGES, not as tensors: a second reference to the tensor
+        # makes autograd's AccumulateGrad clone the gradient instead of adopting it as .grad, and that clone runs on
+        # the main stream BEFORE the side stream has written it. Round 2 kept the bias gradient as a tensor: inside
+        # a captured step the stem's .bias.grad was therefore the PREVIOUS replay's sum (found by the bit-exact
+        # graph == eager check of the deterministic mode).
+        _overlap["keep"][x.device.index].append((dy, x, res[0].untyped_storage(),
+                                                 None if res[1] is None else res[1].untyped_storage()))
+        if res[1] is not None and out_db is None:
+            # belt and braces for a free-standing bias gradient (only top-level convs have a bias; the stem's wgrad
+            # is the last kernel of backward): whatever autograd does with it on the main stream is ordered after
+            # the side stream
+            torch.cuda.current_stream(x.device).wait_stream(side)
         return res
     N, H, W, C = x.shape
     Nd, P, Q, K = dy.shape
