@@ -753,8 +753,13 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
-    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, stats,
-                       stats_fused, fin, 1, nullptr, 2, relu);
+    // With so few MMAs per output the epilogue IS the kernel, and the fused statistics make it ~10x longer per
+    // 16-column chunk (ncu, ImageNet-shape stem: 3600 instructions per warp and tile, issue slots 31 % busy, tensor
+    // pipe 8 %, 1.2 TB/s). B200_IM2COL_FUSED_STATS=0 leaves the sums to the stand-alone statistics kernel.
+    static const int fuse_env = env_int("B200_IM2COL_FUSED_STATS", 1);
+    const bool fuse = fuse_env != 0;
+    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, fuse ? stats : nullptr,
+                       stats_fused, fuse ? fin : nullptr, 1, nullptr, 2, relu);
   }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {
@@ -1296,10 +1301,15 @@ static int run_wgrad_tc(const void* act, int Nact, int Ha, int Wa, int C, const 
 }
 
 // geometry shared by b200_conv2d_wgrad and its workspace query
-static int dbias_pix_per_block(size_t npix) {
+static int dbias_pix_per_block(size_t npix, int K) {
   // ONE block per SM: every block ends with K same-address atomics, which serialise (592 blocks took 46 us
   // for the 42 MB stem gradient in round 2's launch list, most of it in the atomics)
-  return (int)std::max<size_t>(64, (npix + (size_t)num_sms() - 1) / (size_t)num_sms());
+  // ... but a block streams only ~1.3 TB/s / 148 with its 256 x 8 16-byte loads in flight: tensors far beyond the
+  // WRN stem's 42 MB (the 3.3 GB ImageNet-shape stem gradient took 2.5 ms per step, 5x its HBM time) get up to 8
+  // blocks per SM, one more per 64 MB
+  const size_t per_sm = std::min<size_t>(8, std::max<size_t>(1, (npix * (size_t)K * 2) >> 26));
+  const size_t blocks = (size_t)num_sms() * per_sm;
+  return (int)std::max<size_t>(64, (npix + blocks - 1) / blocks);
 }
 static int direct_wgrad_chunks(int total, size_t npix, int* pix_per_chunk) {
   const int bx = (total + 255) / 256;
@@ -1315,7 +1325,7 @@ static void wgrad_det_regions(int N, int H, int W, int C, int K, int R, int S, i
                               size_t* dbias_bytes, size_t* part_bytes) {
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   const size_t npix = (size_t)N * P * Q;
-  const int ppc = dbias_pix_per_block(npix);
+  const int ppc = dbias_pix_per_block(npix, K);
   *dbias_bytes = align_up((npix + ppc - 1) / ppc * (size_t)K * 4, 1024);
   *part_bytes = 0;
   WgradDet dry = {nullptr, 0, true, 1};
@@ -1369,7 +1379,7 @@ extern "C" int b200_conv2d_wgrad(const void* dy, const void* x, float* dw_krsc, 
                  part_bytes, false, 1};
   if (dbias) {
     B200_REQUIRE(K % 8 == 0, "conv2d_wgrad: dbias needs K %% 8 == 0 (K=%d)", K);
-    const int ppc = dbias_pix_per_block(npix);
+    const int ppc = dbias_pix_per_block(npix, K);
     const unsigned nblk = (unsigned)((npix + ppc - 1) / ppc);
     const bool part = det && nblk > 1;
     if (!part) B200_CUDA(cudaMemsetAsync(dbias, 0, (size_t)K * 4, st));
@@ -1902,6 +1912,20 @@ extern "C" int b200_maxpool_fwd(const void* x, void* y, void* argmax, int N, int
                                 int stride, int pad, b200_stream_t stream) {
   B200_REQUIRE(x && y && C % 8 == 0 && stride >= 1 && k * k <= 255, "maxpool_fwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  // compile-time window / stride variants (k3 s2: the ImageNet-style stem pool; k2 s2; k3 s1): one block row per
+  // output row, 256 threads over its (column, channel group) pairs
+  const long long rows_f = (long long)N * d.P;
+  const int per_row_f = d.Q * (C / 8);
+  if (rows_f <= 0x7fffffffLL && per_row_f > 0 && ((k == 3 && (stride == 2 || stride == 1)) || (k == 2 && stride == 2))) {
+    const dim3 grid((unsigned)rows_f, (unsigned)std::min(64, (per_row_f + 255) / 256));
+#define B200_MP_FWD(K_, S_) launch_k(maxpool_fwd_ks_kernel<K_, S_>, grid, 256, 0, as_stream(stream), (const bf16*)x, (bf16*)y, reinterpret_cast<uint8_t*>(argmax), d)
+    if (k == 3 && stride == 2) B200_MP_FWD(3, 2);
+    else if (k == 3) B200_MP_FWD(3, 1);
+    else B200_MP_FWD(2, 2);
+#undef B200_MP_FWD
+    B200_LAUNCH_CHECK("maxpool_fwd_ks_kernel");
+    return 0;
+  }
   launch_k(maxpool_fwd_kernel, ew_grid((size_t)N * d.P * d.Q * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)x, (bf16*)y, reinterpret_cast<uint8_t*>(argmax), d);
   B200_LAUNCH_CHECK("maxpool_fwd_kernel");
   return 0;
@@ -1911,6 +1935,18 @@ extern "C" int b200_maxpool_bwd(const void* dy, const void* argmax, void* dx, in
                                 int stride, int pad, b200_stream_t stream) {
   B200_REQUIRE(dy && argmax && dx && stride >= 1 && C % 8 == 0, "maxpool_bwd: bad arguments");
   PoolDims d = pool_dims(N, H, W, C, k, stride, pad);
+  const long long rows_b = (long long)N * H;
+  const int per_row_b = W * (C / 8);
+  if (rows_b <= 0x7fffffffLL && per_row_b > 0 && ((k == 3 && (stride == 2 || stride == 1)) || (k == 2 && stride == 2))) {
+    const dim3 grid((unsigned)rows_b, (unsigned)std::min(64, (per_row_b + 255) / 256));
+#define B200_MP_BWD(K_, S_) launch_k(maxpool_bwd_ks_kernel<K_, S_>, grid, 256, 0, as_stream(stream), (const bf16*)dy, reinterpret_cast<const uint8_t*>(argmax), (bf16*)dx, d)
+    if (k == 3 && stride == 2) B200_MP_BWD(3, 2);
+    else if (k == 3) B200_MP_BWD(3, 1);
+    else B200_MP_BWD(2, 2);
+#undef B200_MP_BWD
+    B200_LAUNCH_CHECK("maxpool_bwd_ks_kernel");
+    return 0;
+  }
   launch_k(maxpool_bwd_kernel, ew_grid((size_t)N * H * W * C / 8), EW_THREADS, 0, as_stream(stream), (const bf16*)dy, reinterpret_cast<const uint8_t*>(argmax), (bf16*)dx, d);
   B200_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;

@@ -400,10 +400,12 @@ def test_subsample_upsample():
     assert torch.equal(dx, ref.bfloat16())
 
 
-@pytest.mark.parametrize("k,s,p,H", [(8, 1, 0, 8), (3, 2, 1, 16), (2, 2, 0, 8)])
+@pytest.mark.parametrize("k,s,p,H", [(8, 1, 0, 8), (3, 2, 1, 16), (2, 2, 0, 8),
+                                     # compile-time window / stride kernels on odd extents; generic fallback (k = 5)
+                                     (3, 2, 1, 15), (3, 2, 0, 17), (3, 1, 1, 12), (2, 2, 0, 14), (5, 2, 2, 16)])
 def test_pools(k, s, p, H):
     ops, _ = _ops()
-    x = torch.randn(2, H, H, 32, device="cuda").bfloat16()
+    x = torch.randn(2, H, H, 40 if H % 2 else 32, device="cuda").bfloat16()
     # NCHW-contiguous reference tensors (torch's channels_last avg_pool2d backward differs)
     xa = nhwc(x).float().contiguous().requires_grad_(True)
     ref = F.avg_pool2d(xa, k, s, p)
@@ -426,6 +428,23 @@ def test_pools(k, s, p, H):
     F.max_pool2d(xtm, k, s, p).backward(nhwc(dy).float().contiguous())
     _, amt = ops.maxpool_fwd(xt, k, s, p, want_argmax=True)
     assert rel_l2(nhwc(ops.maxpool_bwd(dy, amt, tuple(xt.shape), k, s, p)), xtm.grad) < 4e-3
+
+
+def test_maxpool_imagenet_stem_shape_with_ties():
+    """k3 s2 p1 over a 112 x 112 map (the ImageNet-style stem pool), values from a 4-symbol alphabet so that nearly
+    every window has ties: outputs equal torch's, the gradient lands on the FIRST maximum of every window."""
+    ops, _ = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randint(0, 4, (4, 112, 112, 64), device="cuda", generator=g).bfloat16()
+    xm = nhwc(x).float().contiguous().requires_grad_(True)
+    ref = F.max_pool2d(xm, 3, 2, 1)
+    y, am = ops.maxpool_fwd(x, 3, 2, 1, want_argmax=True)
+    assert torch.equal(nhwc(y).float(), ref)
+    dy = torch.randn(4, 56, 56, 64, device="cuda", generator=g).bfloat16()
+    ref.backward(nhwc(dy).float().contiguous())
+    dx = ops.maxpool_bwd(dy, am, tuple(x.shape), 3, 2, 1)
+    assert rel_l2(nhwc(dx), xm.grad) < 4e-3
+    assert torch.equal(nhwc(dx).float() != 0, xm.grad != 0)
 
 
 def test_linear_and_ce():
