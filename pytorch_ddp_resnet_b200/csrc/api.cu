@@ -567,6 +567,24 @@ static int run_conv_tc(const void* act, int Nact, int Ha, int Wa, int Cin, const
     return run_conv_tc(act, Nact, Ha, Wa, Cin, wmat, Cout, wcols, taps, out, nullptr, bias, Nimg, P, Q, st, nullptr,
                        nullptr, nullptr, cstride, phases, es, relu, nullptr);
   };
+  // The per-channel sums cost the epilogue ~200 instructions per 16-column chunk against ~30 for the plain one.
+  // Behind a long main loop (3x3 filters: >= 1152 MACs per output) that hides under the next tile's MMAs; behind a
+  // short one (1x1 filters of the bottleneck blocks, im2col'd stems) the epilogue IS the kernel. Measured at the
+  // ImageNet shapes, batch 256 (tools/bench_conv.py): 128 -> 512 1x1 @56x56 fprop 244 us plain, 637 us with fused
+  // sums, 165 us for the stand-alone statistics kernel on its output; its dgrad 244 / 1048 us; at a reduction
+  // length of 512 the two ways tie, above it the fused sums cost 8 - 40 us. The fused sums cost ~0.5 us per MB of
+  // output there, the stand-alone pass ~0.2 us per MB + ~8 us of launch and drain: on small tensors (ResNet-20,
+  // ResNet-v2-164: launch-bound) fusing still wins. Hence: NOT fused below 512 MACs per output
+  // (B200_FUSED_STATS_MIN_K) when the output is larger than 32 MB (B200_FUSED_STATS_MAX_MB).
+  static const int fused_min_k = env_int("B200_FUSED_STATS_MIN_K", 512);
+  static const int fused_max_mb = env_int("B200_FUSED_STATS_MAX_MB", 32);
+  if ((stats || bb) && taps.n * Cin < fused_min_k &&
+      (size_t)Nimg * P * Q * Cout * 2 > ((size_t)fused_max_mb << 20)) {
+    if (bb) return plain_without_bb();
+    stats = nullptr;
+    finp = nullptr;
+    memset(&fin, 0, sizeof(fin));
+  }
   if (bb) {
     B200_REQUIRE(stats && stats_fused && finp && residual && es == 2 && !bias && !relu,
                  "conv_tc: the fused BN backward needs x, a statistics workspace and a plain bf16 dgrad");
@@ -753,13 +771,8 @@ static int conv2d_fprop_impl(const void* x, const void* w_krsc, const float* bia
     TapTable tt;
     memset(&tt, 0, sizeof(tt));
     tt.n = 1;
-    // With so few MMAs per output the epilogue IS the kernel, and the fused statistics make it ~10x longer per
-    // 16-column chunk (ncu, ImageNet-shape stem: 3600 instructions per warp and tile, issue slots 31 % busy, tensor
-    // pipe 8 %, 1.2 TB/s). B200_IM2COL_FUSED_STATS=0 leaves the sums to the stand-alone statistics kernel.
-    static const int fuse_env = env_int("B200_IM2COL_FUSED_STATS", 1);
-    const bool fuse = fuse_env != 0;
-    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, fuse ? stats : nullptr,
-                       stats_fused, fuse ? fin : nullptr, 1, nullptr, 2, relu);
+    return run_conv_tc(col, N, P, Q, kpad, wpad, K, kpad, tt, y, residual, bias, N, P, Q, st, stats,
+                       stats_fused, fin, 1, nullptr, 2, relu);
   }
   B200_REQUIRE(tc || algo != B200_ALGO_TC, "conv2d_fprop: shape not supported by the tcgen05 path");
   if (!tc) {

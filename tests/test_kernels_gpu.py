@@ -244,6 +244,10 @@ BNBWD_SHAPES = [
     (8, 32, 160, 320, 1, 2, 0, None),    # 1x1 stride 2 (projection): fused or not, the result must agree
     (4, 16, 64, 128, 3, 1, 1, True),
     (2, 8, 24, 40, 3, 1, 1, False),      # channel counts without a tensor-core tile: plain dgrad, sums is None
+    (4, 16, 512, 128, 1, 1, 0, True),    # 1x1, reduction length 128 but a small tensor: still fused
+    (64, 32, 512, 128, 1, 1, 0, False),  # ... 67 MB of output behind 128 MACs each: the epilogue sums would outlast
+                                         # the MMAs, left to the stand-alone reduce pass
+    (64, 32, 128, 512, 1, 1, 0, True),   # reduction length 512: fused at any size
 ]
 
 

@@ -19,6 +19,15 @@ SHAPES = [  # N, H, W, C, K, R, stride, pad  (WRN-28-10, batch 128)
     (128, 16, 16, 160, 320, 1, 1, 0),
 ]
 
+IMAGENET_SHAPES = [  # WRN-50-2-like bottleneck stacks at 224 x 224, batch 256 (bench.py --config wrn50-imagenet)
+    (256, 56, 56, 512, 128, 1, 1, 0), (256, 56, 56, 128, 128, 3, 1, 1), (256, 56, 56, 128, 512, 1, 1, 0),
+    (256, 28, 28, 1024, 256, 1, 1, 0), (256, 28, 28, 256, 256, 3, 1, 1), (256, 28, 28, 256, 1024, 1, 1, 0),
+    (256, 14, 14, 2048, 512, 1, 1, 0), (256, 14, 14, 512, 512, 3, 1, 1), (256, 14, 14, 512, 2048, 1, 1, 0),
+    (256, 7, 7, 4096, 1024, 1, 1, 0), (256, 7, 7, 1024, 1024, 3, 1, 1), (256, 7, 7, 1024, 4096, 1, 1, 0),
+]
+if os.environ.get("BENCH_CONV_SET") == "imagenet":
+    SHAPES = IMAGENET_SHAPES
+
 
 def timeit(fn, iters=24, warm=3):
     """CUDA-event time per launch with the launches captured in a CUDA graph (no host overhead)."""
