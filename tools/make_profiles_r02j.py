@@ -25,6 +25,9 @@ for name in ("bench_det", "bench_configs"):
     pth = f"{G}/r02j_{name}.json"
     if os.path.exists(pth):
         lines.update(json.load(open(pth)))
+for n in (2, 4, 8):
+    if os.path.exists(f"{G}/r02j_n{n}.log"):
+        lines[f"n{n}"] = last_json(f"{G}/r02j_n{n}.log")
 json.dump(lines, open(f"{P}/r02j_bench_lines.json", "w"), indent=1)
 for tag in ("launches", "launches_warm"):
     src = f"{G}/r02j_{tag}.csv"
