@@ -28,6 +28,9 @@ for name in ("bench_det", "bench_configs"):
 for n in (2, 4, 8):
     if os.path.exists(f"{G}/r02j_n{n}.log"):
         lines[f"n{n}"] = last_json(f"{G}/r02j_n{n}.log")
+for c in ("v2-164", "wrn50-imagenet"):
+    if os.path.exists(f"{G}/r02j_n2_{c}.log"):
+        lines[f"n2_config_{c}"] = last_json(f"{G}/r02j_n2_{c}.log")
 json.dump(lines, open(f"{P}/r02j_bench_lines.json", "w"), indent=1)
 for tag in ("launches", "launches_warm"):
     src = f"{G}/r02j_{tag}.csv"
