@@ -53,6 +53,28 @@ def test_library_exports_every_header_symbol():
     assert lib.b200_conv2d_workspace_bytes(1, 128, 32, 32, 160, 320, 3, 3, 2, 1, flag) == 128 * 32 * 32 * 160 * 2
 
 
+def test_deterministic_mode_flag_plumbing():
+    """ops.deterministic() / torch.use_deterministic_algorithms / B200_DETERMINISTIC or the flag into every conv
+    algo argument (host logic only: no kernel runs here)."""
+    from pytorch_ddp_resnet_b200 import _lib, ops
+    base = ops.conv_algo()
+    assert not ops.is_deterministic() and ops._algo_flags(None) == base
+    with ops.deterministic():
+        assert ops.is_deterministic()
+        assert ops._algo_flags(None) == base | _lib.ALGO_DETERMINISTIC
+        assert ops._algo_flags(_lib.ALGO_DIRECT) == _lib.ALGO_DIRECT | _lib.ALGO_DETERMINISTIC
+        with ops.deterministic(False):
+            assert ops._algo_flags(_lib.ALGO_TC) == _lib.ALGO_TC
+        assert ops.is_deterministic()
+    assert not ops.is_deterministic()
+    torch.use_deterministic_algorithms(True)
+    try:
+        assert ops.is_deterministic() and ops._algo_flags(None) & _lib.ALGO_DETERMINISTIC
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert ops._algo_flags(None) == base
+
+
 def test_no_cpu_fallback():
     from pytorch_ddp_resnet_b200._lib import B200Error
     from pytorch_ddp_resnet_b200.architectures.resnet import ResNet
